@@ -1,0 +1,374 @@
+// assemble.cuh -- K4 fused cull + occlusion, K6 order-preserving CSR fill, and
+// the visibility / occlusion query kernels.
+//
+// Replaces the Python row loop of get_form_factor_matrix (reference
+// src/flux/form_factors.py:45-70) and the per-row Embree stream call
+// (src/flux/shape.py:349-398).
+#pragma once
+#include "common.cuh"
+#include "trace.cuh"
+
+namespace fluxb200 {
+
+constexpr int kTraceWarps = 8;
+constexpr int kTraceThreads = kTraceWarps * 32;
+constexpr int kChunkCols = 1024; // sorted columns per warp work unit = 32 ballot words
+
+#define FB_PI 3.141592653589793
+
+// Un-normalised numerator max(0, n_i.d) * max(0, -n_j.d), d = p_j - p_i, in
+// double from the shape model's own P, N (form_factors.py:46-47 evaluated
+// directly); explicit FMA chain = the oracle's dot3d.
+template <class T>
+__device__ __forceinline__ double numerator(const Real4<T> &Pi, const Real4<T> &Ni, const Real4<T> &Pj,
+                                            const Real4<T> &Nj, double &dx, double &dy, double &dz) {
+    dx = __dsub_rn((double)Pj.x, (double)Pi.x);
+    dy = __dsub_rn((double)Pj.y, (double)Pi.y);
+    dz = __dsub_rn((double)Pj.z, (double)Pi.z);
+    double a = __fma_rn((double)Ni.x, dx, __fma_rn((double)Ni.y, dy, __dmul_rn((double)Ni.z, dz)));
+    double b = -__fma_rn((double)Nj.x, dx, __fma_rn((double)Nj.y, dy, __dmul_rn((double)Nj.z, dz)));
+    a = a > 0.0 ? a : 0.0;
+    b = b > 0.0 ? b : 0.0;
+    return __dmul_rn(a, b);
+}
+
+template <class T> __device__ __forceinline__ bool survives_cull(double num, T eps);
+template <> __device__ __forceinline__ bool survives_cull<float>(double num, float eps) {
+    const float v = __double2float_rn(num); // abs(row_data) > eps in the shape model's dtype
+    return v > eps || -v > eps;
+}
+template <> __device__ __forceinline__ bool survives_cull<double>(double num, double eps) {
+    return num > eps || -num > eps;
+}
+
+template <class T> __device__ __forceinline__ Real4<T> load_real4(const Real4<T> *p);
+template <> __device__ __forceinline__ Real4<float> load_real4<float>(const Real4<float> *p) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    return Real4<float>{v.x, v.y, v.z, v.w};
+}
+template <> __device__ __forceinline__ Real4<double> load_real4<double>(const Real4<double> *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return Real4<double>{a.x, a.y, b.x, b.y};
+}
+
+template <class T> struct TraceArgs {
+    const Real4<T> *faceP, *faceN;  // per face, original order
+    const int *rows;                // m face ids (I)
+    const Real4<T> *colP, *colN;    // n columns gathered in leaf (Morton) order
+    const int *col_face, *col_leaf; // face id / leaf position of sorted column s
+    int m, n, nwords;               // nwords = ceil(n/32)
+    int nseg, chunks_per_seg;       // column segmentation of a row over CTAs
+    T eps;
+    const float4 *nodes, *tri;
+    int nnodes, ntop;
+    uint32_t *bits;                 // m x nwords visibility words, sorted-column order
+    uint32_t *row_counts;           // m
+    unsigned long long *tested;     // 1
+};
+
+// K4.  One CTA = one row (source face i) x one segment of Morton-ordered
+// columns.  Each warp owns chunks of 1024 columns:
+//   phase 1  geometric cull, 32 coalesced column loads per lane, survivors as
+//            32 ballot words (lane k keeps word k);
+//   phase 2  survivors are compacted 32 at a time (prefix of popcounts +
+//            find-nth-set-bit) so every lane of a trace batch holds a ray;
+//            occluded rays clear their bit in the warp's shared words;
+//   phase 3  the 32 final words go out as one coalesced 128-byte store.
+template <class T>
+__global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs<T> A) {
+    extern __shared__ float4 smem_top[];
+    __shared__ uint32_t words_s[kTraceWarps][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < 2 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
+    __syncthreads();
+    BvhView bvh{A.nodes, smem_top, A.tri, A.ntop, A.nnodes};
+
+    const int r = blockIdx.x / A.nseg, seg = blockIdx.x - r * A.nseg;
+    const int i = A.rows[r];
+    const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
+    const int nchunks = (A.n + kChunkCols - 1) / kChunkCols;
+    const int c_begin = seg * A.chunks_per_seg, c_end = min(nchunks, c_begin + A.chunks_per_seg);
+    unsigned count = 0, tested = 0;
+
+    for (int c = c_begin + warp; c < c_end; c += kTraceWarps) {
+        const int s0 = c * kChunkCols;
+        // ---- phase 1: cull -----------------------------------------------------
+        uint32_t myword = 0;
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int s = s0 + k * 32 + lane;
+            bool keep = false;
+            if (s < A.n) {
+                const Real4<T> Pj = load_real4<T>(A.colP + s), Nj = load_real4<T>(A.colN + s);
+                double dx, dy, dz;
+                double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
+                if (A.col_face[s] == i) num = 0.0; // row_data[i == J] = 0
+                keep = survives_cull<T>(num, A.eps);
+            }
+            const uint32_t w = __ballot_sync(0xffffffffu, keep);
+            if (lane == k) myword = w;
+        }
+        // ---- phase 2: trace the survivors, 32 rays per batch ---------------------
+        uint32_t incl = __popc(myword);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        tested += total;
+        words_s[warp][lane] = myword;
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t want = base + lane; // index of my survivor within the chunk
+            // smallest k with incl[k] > want (binary search over the lanes' prefix)
+            int k = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, k + step - 1);
+                if (v <= want) k += step;
+            }
+            const uint32_t wk = __shfl_sync(0xffffffffu, myword, k);
+            const uint32_t before = __shfl_sync(0xffffffffu, incl - __popc(myword), k);
+            if (want < total) {
+                const int bit = __fns(wk, 0, (int)(want - before) + 1);
+                const int s = s0 + k * 32 + bit;
+                const Real4<T> Pj = load_real4<T>(A.colP + s);
+                Ray ray;
+                bool visible = true; // masked pairs: "vis by default" (shape.py:392)
+                if (setup_ray(Pi, Pj, ray))
+                    visible = target_visible(bvh, ray, A.col_leaf[s], A.col_face[s]);
+                if (!visible) atomicAnd(&words_s[warp][k], ~(1u << bit));
+            }
+        }
+        __syncwarp();
+        // ---- phase 3: publish -----------------------------------------------------
+        const uint32_t fin = words_s[warp][lane];
+        const int wi = c * 32 + lane;
+        if (wi < A.nwords) A.bits[(size_t)r * A.nwords + wi] = fin;
+        count += __popc(fin);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+    if (lane == 0) {
+        if (count) atomicAdd(&A.row_counts[r], count);
+        if (tested) atomicAdd(A.tested, (unsigned long long)tested);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6: CSR fill.  One CTA per (row, part); columns are visited in ORIGINAL J
+// order so every row comes out with ascending column positions
+// (form_factors.py:52, 69).  The row's visibility words (sorted-column order)
+// are staged in shared memory and looked up through rank_of_pos.
+// ---------------------------------------------------------------------------
+constexpr int kFillThreads = 256;
+
+template <class T> struct FillArgs {
+    const Real4<T> *faceP, *faceN;
+    const int *rows;        // m
+    const int *cols;        // n face ids in original J order
+    const int *rank_of_pos; // n: sorted position of original column q
+    int m, n, nwords;
+    const uint32_t *bits;
+    const int64_t *indptr;  // m + 1 (device, int64)
+    T *data;
+    void *indices;          // int32 or int64
+    int index_width;
+    int bits_in_smem;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A) {
+    extern __shared__ uint32_t bits_s[];
+    __shared__ uint32_t warp_tot[kFillThreads / 32];
+    __shared__ uint32_t running_s;
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row_begin = A.indptr[r];
+    if (A.indptr[r + 1] == row_begin) return;
+    const uint32_t *gbits = A.bits + (size_t)r * A.nwords;
+    if (A.bits_in_smem) {
+        for (int k = threadIdx.x; k < A.nwords; k += kFillThreads) bits_s[k] = gbits[k];
+    }
+    if (threadIdx.x == 0) running_s = 0;
+    __syncthreads();
+    const uint32_t *bits = A.bits_in_smem ? bits_s : gbits;
+    const int i = A.rows[r];
+    const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
+    for (int q0 = 0; q0 < A.n; q0 += kFillThreads) {
+        const int q = q0 + threadIdx.x;
+        bool set = false;
+        if (q < A.n) {
+            const int s = A.rank_of_pos[q];
+            set = (bits[s >> 5] >> (s & 31)) & 1u;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, set);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = running_s;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (set) {
+            const int j = A.cols[q];
+            const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
+            double dx, dy, dz;
+            double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
+            if (j == i) num = 0.0;
+            const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
+            const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                 // :62
+            const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj.w), sden); // :63-64
+            const int64_t dst = row_begin + off + __popc(bal & ((1u << lane) - 1u));
+            A.data[dst] = (T)v;
+            if (A.index_width == 4) reinterpret_cast<int32_t *>(A.indices)[dst] = q;
+            else reinterpret_cast<int64_t *>(A.indices)[dst] = q;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kFillThreads / 32; ++w) t += warp_tot[w];
+            running_s += t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// query kernels (TrimeshShapeModel hooks)
+// ---------------------------------------------------------------------------
+template <class T>
+__global__ void visibility_kernel(const Real4<T> *__restrict__ faceP, const int *__restrict__ rows, int m,
+                                  const int *__restrict__ cols, int n, const int *__restrict__ face_leaf,
+                                  const float4 *nodes, const float4 *tri, int nnodes, int nf,
+                                  int bruteforce, uint8_t *__restrict__ vis) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)m * n) return;
+    const int p = (int)(idx / n), q = (int)(idx - (int64_t)p * n);
+    const int i = rows[p], j = cols[q];
+    const Real4<T> Pi = load_real4<T>(faceP + i), Pj = load_real4<T>(faceP + j);
+    Ray ray;
+    bool visible = true;
+    if (setup_ray(Pi, Pj, ray)) {
+        if (bruteforce) visible = target_visible_bruteforce(tri, nf, ray, face_leaf[j], j);
+        else {
+            BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+            visible = target_visible(bvh, ray, face_leaf[j], j);
+        }
+    }
+    vis[idx] = visible ? 1 : 0;
+}
+
+// origin P[i] + eps*N[i] (shape.py:410), direction D as given; any hit in [0, inf]
+template <class T>
+__global__ void occluded_kernel(const Real4<T> *__restrict__ faceP, const Real4<T> *__restrict__ faceN,
+                                const int *__restrict__ rows, int m, const T *__restrict__ D, int nd,
+                                int mode, const float4 *nodes, const float4 *tri, int nnodes,
+                                uint8_t *__restrict__ occ) {
+    const int cols = mode == 2 ? nd : 1;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)m * cols) return;
+    const int p = (int)(idx / cols), c = (int)(idx - (int64_t)p * cols);
+    const int i = rows[p];
+    const Real4<T> Pi = load_real4<T>(faceP + i), Ni = load_real4<T>(faceN + i);
+    const T eps = (T)ray_eps();
+    const T *d = mode == 0 ? D : (mode == 1 ? D + 3 * (size_t)p : D + 3 * (size_t)c);
+    Ray ray;
+    ray.ox = (float)rn_add<T>(Pi.x, rn_mul<T>(eps, Ni.x));
+    ray.oy = (float)rn_add<T>(Pi.y, rn_mul<T>(eps, Ni.y));
+    ray.oz = (float)rn_add<T>(Pi.z, rn_mul<T>(eps, Ni.z));
+    ray.dx = (float)d[0];
+    ray.dy = (float)d[1];
+    ray.dz = (float)d[2];
+    BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+    occ[idx] = occluded_anyhit(bvh, ray, __int_as_float(0x7f800000), -1, 0x7fffffff) ? 1 : 0;
+}
+
+__global__ void intersect1_kernel(float ox, float oy, float oz, float dx, float dy, float dz,
+                                  const float4 *nodes, const float4 *tri, int nnodes, int *face_out,
+                                  float *t_out) {
+    Ray ray{ox, oy, oz, dx, dy, dz};
+    BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+    float t = __int_as_float(0x7f800000);
+    int face;
+    closest_hit(bvh, ray, t, face);
+    *face_out = face;
+    *t_out = t;
+}
+
+// ---- per-call preparation -----------------------------------------------------
+__global__ void col_keys_kernel(const int *__restrict__ cols, int n, const int *__restrict__ face_leaf,
+                                uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    keys[q] = (uint64_t)(uint32_t)face_leaf[cols[q]];
+    vals[q] = (uint32_t)q;
+}
+
+// sorted position s -> original position pos[s]; gathers the column arrays
+template <class T>
+__global__ void col_gather_kernel(const uint32_t *__restrict__ pos, const int *__restrict__ cols, int n,
+                                  const int *__restrict__ face_leaf, const Real4<T> *__restrict__ faceP,
+                                  const Real4<T> *__restrict__ faceN, Real4<T> *__restrict__ colP,
+                                  Real4<T> *__restrict__ colN, int *__restrict__ col_face,
+                                  int *__restrict__ col_leaf, int *__restrict__ rank_of_pos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int q = (int)pos[s];
+    const int f = cols[q];
+    colP[s] = faceP[f];
+    colN[s] = faceN[f];
+    col_face[s] = f;
+    col_leaf[s] = face_leaf[f];
+    rank_of_pos[q] = s;
+}
+
+// interleave host-side P (nf x 3), N (nf x 3), A (nf) into the packed arrays
+template <class T>
+__global__ void pack_face_kernel(const T *__restrict__ P, const T *__restrict__ N, const T *__restrict__ A,
+                                 int nf, Real4<T> *__restrict__ faceP, Real4<T> *__restrict__ faceN) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    if (P) {
+        faceP[f].x = P[3 * (size_t)f];
+        faceP[f].y = P[3 * (size_t)f + 1];
+        faceP[f].z = P[3 * (size_t)f + 2];
+    }
+    if (A) faceP[f].w = A[f];
+    if (N) {
+        faceN[f].x = N[3 * (size_t)f];
+        faceN[f].y = N[3 * (size_t)f + 1];
+        faceN[f].z = N[3 * (size_t)f + 2];
+        faceN[f].w = (T)0;
+    }
+}
+
+template <class T>
+__global__ void unpack_face_kernel(const Real4<T> *__restrict__ faceP, const Real4<T> *__restrict__ faceN,
+                                   int nf, T *__restrict__ P, T *__restrict__ N, T *__restrict__ A) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    if (P) {
+        P[3 * (size_t)f] = faceP[f].x;
+        P[3 * (size_t)f + 1] = faceP[f].y;
+        P[3 * (size_t)f + 2] = faceP[f].z;
+    }
+    if (A) A[f] = faceP[f].w;
+    if (N) {
+        N[3 * (size_t)f] = faceN[f].x;
+        N[3 * (size_t)f + 1] = faceN[f].y;
+        N[3 * (size_t)f + 2] = faceN[f].z;
+    }
+}
+
+__global__ void counts_to_i64_kernel(const uint32_t *__restrict__ c, int m, int64_t *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) out[r] = (int64_t)c[r];
+}
+
+__global__ void indptr_to_i32_kernel(const int64_t *__restrict__ in, int n, int32_t *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) out[r] = (int32_t)in[r];
+}
+
+} // namespace fluxb200

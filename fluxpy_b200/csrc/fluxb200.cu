@@ -1,0 +1,732 @@
+// fluxb200.cu -- host side of libfluxb200.so: the opaque mesh handle and the
+// C ABI declared in include/fluxb200.h.  All device work of one handle is
+// enqueued on the handle's own stream.
+#include "../../include/fluxb200.h"
+#include "assemble.cuh"
+#include "common.cuh"
+#include "lbvh.cuh"
+#include "prims.cuh"
+#include "trace.cuh"
+
+#include <algorithm>
+#include <string.h>
+#include <vector>
+
+namespace fluxb200 {
+thread_local std::string g_last_error;
+}
+using namespace fluxb200;
+
+struct fluxb200_mesh {
+    int device = 0;
+    int dtype = FLUXB200_F32;
+    size_t nv = 0, nf = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    int num_sms = 148;
+    int max_smem_optin = 48 * 1024;
+
+    DevBuf V, F, V32, faceP, faceN; // geometry
+    // LBVH
+    DevBuf keys, vals, left, right, parent, first, last, box, flags, pre, flag_by_pre, top_before,
+        scene, scalars, nodes, tri, face_leaf;
+    RadixSorter sorter;
+    int nnodes = 0, ntop = 0, max_depth = 0;
+    int top_nodes_opt = 1024;
+    float ms_build = 0.f;
+    float scene_h[7] = {};
+
+    // per-call state
+    DevBuf rows, cols, ckeys, cvals, colP, colN, col_face, col_leaf, rank_of_pos, bits, row_counts,
+        counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout;
+    size_t m = 0, n = 0;
+    int nwords = 0;
+    double eps = 0;
+    int64_t nnz = 0;
+    bool have_count = false;
+    fluxb200_ff_stats stats = {};
+    int trace_mode = 0;
+
+    size_t esize() const { return dtype == FLUXB200_F64 ? 8 : 4; }
+};
+
+namespace {
+
+template <class F> int guarded(F &&f) {
+    try {
+        f();
+        return 0;
+    } catch (const CudaError &e) {
+        set_error(e.msg);
+        return 1;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
+inline int blocks_for(int64_t n, int threads) { return (int)std::max<int64_t>(1, ceil_div(n, threads)); }
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        FB_CUDA(cudaSetDevice(dev));
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+// int64 host index array -> validated int32 (NULL = arange)
+std::vector<int> to_i32(const int64_t *a, size_t len, size_t bound, const char *what) {
+    std::vector<int> out(len);
+    if (!a) {
+        if (len == 0) return out;
+        FB_REQUIRE(len == bound, std::string(what) + ": NULL index array means arange(num_faces)");
+        for (size_t k = 0; k < len; ++k) out[k] = (int)k;
+        return out;
+    }
+    for (size_t k = 0; k < len; ++k) {
+        const int64_t v = a[k];
+        if (v < 0 || (size_t)v >= bound)
+            throw CudaError{std::string(what) + ": index out of range"};
+        out[k] = (int)v;
+    }
+    return out;
+}
+
+template <class T> void build_geometry(fluxb200_mesh *M) {
+    const int nf = (int)M->nf;
+    if (nf)
+        face_geometry_kernel<T><<<blocks_for(nf, 256), 256, 0, M->stream>>>(
+            M->V.as<T>(), M->F.as<int>(), nf, M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>());
+    const size_t n3 = 3 * M->nv;
+    if (n3)
+        vertices_to_f32_kernel<T><<<blocks_for((int64_t)n3, 256), 256, 0, M->stream>>>(
+            M->V.as<T>(), n3, M->V32.as<float>());
+    FB_CUDA(cudaGetLastError());
+}
+
+void bvh_build(fluxb200_mesh *M) {
+    const int n = (int)M->nf;
+    cudaStream_t st = M->stream;
+    M->nnodes = n ? 2 * n - 1 : 0;
+    M->ntop = 0;
+    M->max_depth = 0;
+    if (n == 0) return;
+    const int nn = 2 * n - 1;
+    M->keys.reserve(sizeof(uint64_t) * n);
+    M->vals.reserve(sizeof(uint32_t) * n);
+    M->left.reserve(sizeof(int) * n);
+    M->right.reserve(sizeof(int) * n);
+    M->first.reserve(sizeof(int) * n);
+    M->last.reserve(sizeof(int) * n);
+    M->parent.reserve(sizeof(int) * nn);
+    M->box.reserve(sizeof(float) * 6 * nn);
+    M->flags.reserve(sizeof(int) * n);
+    M->pre.reserve(sizeof(int) * nn);
+    M->flag_by_pre.reserve(sizeof(int) * nn);
+    M->top_before.reserve(sizeof(int) * nn);
+    M->scene.reserve(sizeof(unsigned) * 8);
+    M->scalars.reserve(sizeof(int) * 8);
+    M->nodes.reserve(sizeof(float4) * 2 * nn);
+    M->tri.reserve(sizeof(float4) * 3 * n);
+    M->face_leaf.reserve(sizeof(int) * n);
+
+    FB_CUDA(cudaEventRecord(M->ev[0], st));
+    const unsigned scene_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    FB_CUDA(cudaMemcpyAsync(M->scene.p, scene_init, sizeof(scene_init), cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemsetAsync(M->scalars.p, 0, sizeof(int) * 8, st));
+    FB_CUDA(cudaMemsetAsync(M->parent.p, 0xff, sizeof(int) * nn, st));
+    FB_CUDA(cudaMemsetAsync(M->flags.p, 0, sizeof(int) * n, st));
+    const int B = 256, G = blocks_for(n, B);
+    scene_bounds_kernel<<<G, B, 0, st>>>(M->V32.as<float>(), M->F.as<int>(), n, M->scene.as<unsigned>());
+    morton_kernel<<<G, B, 0, st>>>(M->V32.as<float>(), M->F.as<int>(), n, M->scene.as<unsigned>(),
+                                   M->keys.as<uint64_t>(), M->vals.as<uint32_t>());
+    FB_CUDA(cudaGetLastError());
+    M->sorter.sort(M->keys.as<uint64_t>(), M->vals.as<uint32_t>(), n, 63, st);
+    if (n > 1)
+        karras_kernel<<<blocks_for(n - 1, B), B, 0, st>>>(M->keys.as<uint64_t>(), n, M->left.as<int>(),
+                                                          M->right.as<int>(), M->parent.as<int>(),
+                                                          M->first.as<int>(), M->last.as<int>());
+    refit_kernel<<<G, B, 0, st>>>(M->V32.as<float>(), M->F.as<int>(), n, M->vals.as<uint32_t>(),
+                                  M->left.as<int>(), M->right.as<int>(), M->parent.as<int>(),
+                                  M->scene.as<unsigned>(), M->box.as<float>(), M->flags.as<int>(),
+                                  M->tri.as<float4>(), M->face_leaf.as<int>());
+    const int K = std::max(1, M->top_nodes_opt / 2);
+    const int threshold = n / K; // subtrees with more than n/K leaves: fewer than 2K nodes
+    int *scal = M->scalars.as<int>();
+    preorder_kernel<<<blocks_for(nn, B), B, 0, st>>>(n, M->left.as<int>(), M->parent.as<int>(),
+                                                     M->first.as<int>(), M->last.as<int>(), threshold,
+                                                     M->pre.as<int>(), M->flag_by_pre.as<int>(), scal + 1);
+    scan_exclusive<int, int>(M->flag_by_pre.as<int>(), M->top_before.as<int>(), nn, scal + 0, st);
+    flatten_kernel<<<blocks_for(nn, B), B, 0, st>>>(n, M->left.as<int>(), M->right.as<int>(),
+                                                    M->parent.as<int>(), M->pre.as<int>(),
+                                                    M->top_before.as<int>(), M->flag_by_pre.as<int>(),
+                                                    scal + 0, M->box.as<float>(), M->nodes.as<float4>());
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaEventRecord(M->ev[1], st));
+    int h[2];
+    unsigned sc[8];
+    FB_CUDA(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(sc, M->scene.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    M->ntop = h[0];
+    M->max_depth = h[1];
+    FB_REQUIRE(M->ntop <= std::max(M->top_nodes_opt, 1), "internal: top-node budget exceeded");
+    for (int k = 0; k < 7; ++k) {
+        const unsigned u = sc[k];
+        const unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        memcpy(&M->scene_h[k], &v, 4);
+    }
+    FB_CUDA(cudaEventElapsedTime(&M->ms_build, M->ev[0], M->ev[1]));
+}
+
+template <class T> void set_face_data(fluxb200_mesh *M, const void *P, const void *N, const void *A) {
+    const size_t nf = M->nf;
+    if (!nf || (!P && !N && !A)) return;
+    cudaStream_t st = M->stream;
+    M->qtmp.reserve(sizeof(T) * 7 * nf);
+    T *dP = M->qtmp.as<T>(), *dN = dP + 3 * nf, *dA = dN + 3 * nf;
+    if (P) FB_CUDA(cudaMemcpyAsync(dP, P, sizeof(T) * 3 * nf, cudaMemcpyHostToDevice, st));
+    if (N) FB_CUDA(cudaMemcpyAsync(dN, N, sizeof(T) * 3 * nf, cudaMemcpyHostToDevice, st));
+    if (A) FB_CUDA(cudaMemcpyAsync(dA, A, sizeof(T) * nf, cudaMemcpyHostToDevice, st));
+    pack_face_kernel<T><<<blocks_for((int64_t)nf, 256), 256, 0, st>>>(
+        P ? dP : nullptr, N ? dN : nullptr, A ? dA : nullptr, (int)nf, M->faceP.as<Real4<T>>(),
+        M->faceN.as<Real4<T>>());
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaStreamSynchronize(st));
+}
+
+template <class T> void get_face_data(fluxb200_mesh *M, void *P, void *N, void *A) {
+    const size_t nf = M->nf;
+    if (!nf || (!P && !N && !A)) return;
+    cudaStream_t st = M->stream;
+    M->qtmp.reserve(sizeof(T) * 7 * nf);
+    T *dP = M->qtmp.as<T>(), *dN = dP + 3 * nf, *dA = dN + 3 * nf;
+    unpack_face_kernel<T><<<blocks_for((int64_t)nf, 256), 256, 0, st>>>(
+        M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), (int)nf, dP, dN, dA);
+    FB_CUDA(cudaGetLastError());
+    if (P) FB_CUDA(cudaMemcpyAsync(P, dP, sizeof(T) * 3 * nf, cudaMemcpyDeviceToHost, st));
+    if (N) FB_CUDA(cudaMemcpyAsync(N, dN, sizeof(T) * 3 * nf, cudaMemcpyDeviceToHost, st));
+    if (A) FB_CUDA(cudaMemcpyAsync(A, dA, sizeof(T) * nf, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+}
+
+void upload_index_sets(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n) {
+    FB_REQUIRE(m < (1ull << 31) && n < (1ull << 31), "index sets must have fewer than 2^31 entries");
+    const std::vector<int> rows = to_i32(I, m, M->nf, "I"), cols = to_i32(J, n, M->nf, "J");
+    M->rows.reserve(sizeof(int) * std::max<size_t>(m, 1));
+    M->cols.reserve(sizeof(int) * std::max<size_t>(n, 1));
+    if (m) FB_CUDA(cudaMemcpyAsync(M->rows.p, rows.data(), sizeof(int) * m, cudaMemcpyHostToDevice, M->stream));
+    if (n) FB_CUDA(cudaMemcpyAsync(M->cols.p, cols.data(), sizeof(int) * n, cudaMemcpyHostToDevice, M->stream));
+    FB_CUDA(cudaStreamSynchronize(M->stream)); // the host vectors go out of scope
+}
+
+template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                 double eps, int64_t *row_counts) {
+    cudaStream_t st = M->stream;
+    M->have_count = false;
+    M->stats = fluxb200_ff_stats{};
+    M->stats.pairs_all = (int64_t)m * (int64_t)n;
+    M->m = m;
+    M->n = n;
+    M->eps = eps;
+    M->nwords = (int)ceil_div((int64_t)n, 32);
+    const int launches0 = M->sorter.launches;
+    int launches = 0;
+
+    FB_CUDA(cudaEventRecord(M->ev[0], st));
+    upload_index_sets(M, I, m, J, n);
+    M->row_counts.reserve(sizeof(uint32_t) * std::max<size_t>(m, 1));
+    M->counts64.reserve(sizeof(int64_t) * std::max<size_t>(m, 1));
+    M->indptr.reserve(sizeof(int64_t) * (m + 1));
+    M->tested.reserve(sizeof(unsigned long long) * 2);
+    FB_CUDA(cudaMemsetAsync(M->row_counts.p, 0, sizeof(uint32_t) * std::max<size_t>(m, 1), st));
+    FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 2, st));
+    FB_CUDA(cudaMemsetAsync(M->indptr.p, 0, sizeof(int64_t) * (m + 1), st));
+
+    if (m && n) {
+        // columns in leaf (Morton) order
+        M->ckeys.reserve(sizeof(uint64_t) * n);
+        M->cvals.reserve(sizeof(uint32_t) * n);
+        M->colP.reserve(sizeof(Real4<T>) * n);
+        M->colN.reserve(sizeof(Real4<T>) * n);
+        M->col_face.reserve(sizeof(int) * n);
+        M->col_leaf.reserve(sizeof(int) * n);
+        M->rank_of_pos.reserve(sizeof(int) * n);
+        const int B = 256;
+        col_keys_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(M->cols.as<int>(), (int)n,
+                                                                 M->face_leaf.as<int>(),
+                                                                 M->ckeys.as<uint64_t>(),
+                                                                 M->cvals.as<uint32_t>());
+        int bits = 1;
+        while ((1ull << bits) < M->nf) ++bits;
+        M->sorter.sort(M->ckeys.as<uint64_t>(), M->cvals.as<uint32_t>(), (int)n, bits, st);
+        col_gather_kernel<T><<<blocks_for((int64_t)n, B), B, 0, st>>>(
+            M->cvals.as<uint32_t>(), M->cols.as<int>(), (int)n, M->face_leaf.as<int>(),
+            M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->colP.as<Real4<T>>(),
+            M->colN.as<Real4<T>>(), M->col_face.as<int>(), M->col_leaf.as<int>(),
+            M->rank_of_pos.as<int>());
+        FB_CUDA(cudaGetLastError());
+        launches += 2;
+        M->bits.reserve(sizeof(uint32_t) * m * (size_t)M->nwords);
+    }
+    FB_CUDA(cudaEventRecord(M->ev[1], st));
+
+    if (m && n) {
+        TraceArgs<T> A;
+        A.faceP = M->faceP.as<Real4<T>>();
+        A.faceN = M->faceN.as<Real4<T>>();
+        A.rows = M->rows.as<int>();
+        A.colP = M->colP.as<Real4<T>>();
+        A.colN = M->colN.as<Real4<T>>();
+        A.col_face = M->col_face.as<int>();
+        A.col_leaf = M->col_leaf.as<int>();
+        A.m = (int)m;
+        A.n = (int)n;
+        A.nwords = M->nwords;
+        A.eps = (T)eps;
+        A.nodes = M->nodes.as<float4>();
+        A.tri = M->tri.as<float4>();
+        A.nnodes = M->nnodes;
+        A.ntop = M->ntop;
+        A.bits = M->bits.as<uint32_t>();
+        A.row_counts = M->row_counts.as<uint32_t>();
+        A.tested = M->tested.as<unsigned long long>();
+        const int nchunks = (int)ceil_div((int64_t)n, kChunkCols);
+        const int max_seg = (int)ceil_div(nchunks, kTraceWarps);
+        const int64_t target_ctas = (int64_t)M->num_sms * 16;
+        int nseg = (int)std::min<int64_t>(max_seg, std::max<int64_t>(1, ceil_div(target_ctas, (int64_t)m)));
+        A.chunks_per_seg = (int)ceil_div(nchunks, nseg);
+        A.nseg = (int)ceil_div(nchunks, A.chunks_per_seg);
+        const int64_t grid = (int64_t)m * A.nseg;
+        FB_REQUIRE(grid < (1ll << 31), "too many row segments for one launch");
+        const size_t smem = sizeof(float4) * 2 * (size_t)M->ntop;
+        FB_REQUIRE((int)smem + 2048 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
+        FB_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)std::max<size_t>(smem, 1024)));
+        trace_kernel<T><<<(unsigned)grid, kTraceThreads, smem, st>>>(A);
+        FB_CUDA(cudaGetLastError());
+        launches += 1;
+        M->stats.trace_launches = 1;
+    }
+    FB_CUDA(cudaEventRecord(M->ev[2], st));
+
+    if (m) {
+        counts_to_i64_kernel<<<blocks_for((int64_t)m, 256), 256, 0, st>>>(M->row_counts.as<uint32_t>(),
+                                                                         (int)m, M->counts64.as<int64_t>());
+        scan_exclusive<int64_t, int64_t>(M->counts64.as<int64_t>(), M->indptr.as<int64_t>(), (int64_t)m,
+                                         M->indptr.as<int64_t>() + m, st);
+        launches += 2;
+    }
+    FB_CUDA(cudaEventRecord(M->ev[3], st));
+    int64_t nnz = 0;
+    unsigned long long tested = 0;
+    FB_CUDA(cudaMemcpyAsync(&nnz, M->indptr.as<int64_t>() + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(&tested, M->tested.p, sizeof(tested), cudaMemcpyDeviceToHost, st));
+    if (row_counts && m)
+        FB_CUDA(cudaMemcpyAsync(row_counts, M->counts64.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    M->nnz = nnz;
+    M->stats.nnz = nnz;
+    M->stats.pairs_tested = (int64_t)tested;
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_prepare, M->ev[0], M->ev[1]));
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_trace, M->ev[1], M->ev[2]));
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_scan, M->ev[2], M->ev[3]));
+    M->stats.kernel_launches = launches + (M->sorter.launches - launches0);
+    M->have_count = true;
+}
+
+template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destination, void *indptr,
+                                void *indices, void *data) {
+    FB_REQUIRE(M->have_count, "fluxb200_ff_fill: no preceding fluxb200_ff_count on this handle");
+    FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
+    FB_REQUIRE(destination >= 0 && destination <= 2, "destination must be 0, 1 or 2");
+    if (index_width == 4)
+        FB_REQUIRE(M->nnz < (1ll << 31) && M->n < (1ull << 31), "int32 indices cannot hold this matrix");
+    cudaStream_t st = M->stream;
+    const size_t m = M->m, n = M->n;
+    const int64_t nnz = M->nnz;
+    T *d_data;
+    void *d_indices;
+    if (destination == 1) {
+        d_data = reinterpret_cast<T *>(data);
+        d_indices = indices;
+    } else {
+        M->out_data.reserve(sizeof(T) * std::max<int64_t>(nnz, 1));
+        M->out_indices.reserve((size_t)index_width * std::max<int64_t>(nnz, 1));
+        d_data = M->out_data.as<T>();
+        d_indices = M->out_indices.p;
+    }
+    FB_CUDA(cudaEventRecord(M->ev[0], st));
+    int launches = 0;
+    if (m && n && nnz) {
+        FillArgs<T> A;
+        A.faceP = M->faceP.as<Real4<T>>();
+        A.faceN = M->faceN.as<Real4<T>>();
+        A.rows = M->rows.as<int>();
+        A.cols = M->cols.as<int>();
+        A.rank_of_pos = M->rank_of_pos.as<int>();
+        A.m = (int)m;
+        A.n = (int)n;
+        A.nwords = M->nwords;
+        A.bits = M->bits.as<uint32_t>();
+        A.indptr = M->indptr.as<int64_t>();
+        A.data = d_data;
+        A.indices = d_indices;
+        A.index_width = index_width;
+        size_t smem = sizeof(uint32_t) * (size_t)M->nwords;
+        A.bits_in_smem = (int)smem + 1024 <= M->max_smem_optin;
+        if (!A.bits_in_smem) smem = 0;
+        FB_CUDA(cudaFuncSetAttribute(fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)std::max<size_t>(smem, 1024)));
+        fill_kernel<T><<<(unsigned)m, kFillThreads, smem, st>>>(A);
+        FB_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    void *d_indptr = M->indptr.p;
+    if (index_width == 4) {
+        M->indptr32.reserve(sizeof(int32_t) * (m + 1));
+        indptr_to_i32_kernel<<<blocks_for((int64_t)m + 1, 256), 256, 0, st>>>(
+            M->indptr.as<int64_t>(), (int)(m + 1), M->indptr32.as<int32_t>());
+        d_indptr = M->indptr32.p;
+        ++launches;
+    }
+    FB_CUDA(cudaEventRecord(M->ev[1], st));
+    if (destination == 0) {
+        FB_CUDA(cudaMemcpyAsync(indptr, d_indptr, (size_t)index_width * (m + 1), cudaMemcpyDeviceToHost, st));
+        if (nnz) {
+            FB_CUDA(cudaMemcpyAsync(indices, d_indices, (size_t)index_width * nnz, cudaMemcpyDeviceToHost, st));
+            FB_CUDA(cudaMemcpyAsync(data, d_data, sizeof(T) * nnz, cudaMemcpyDeviceToHost, st));
+        }
+    } else if (destination == 1) {
+        FB_CUDA(cudaMemcpyAsync(indptr, d_indptr, (size_t)index_width * (m + 1), cudaMemcpyDeviceToDevice, st));
+    }
+    FB_CUDA(cudaEventRecord(M->ev[2], st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_fill, M->ev[0], M->ev[1]));
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_d2h, M->ev[1], M->ev[2]));
+    M->stats.kernel_launches += launches;
+}
+
+template <class T> void visibility(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                   uint8_t *vis, int brute) {
+    if (!m || !n) return;
+    cudaStream_t st = M->stream;
+    upload_index_sets(M, I, m, J, n);
+    const int64_t total = (int64_t)m * (int64_t)n;
+    M->qout.reserve((size_t)total);
+    FB_REQUIRE(ceil_div(total, 128) < (1ll << 31), "visibility: too many pairs for one call");
+    visibility_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>(
+        M->faceP.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->cols.as<int>(), (int)n,
+        M->face_leaf.as<int>(), M->nodes.as<float4>(), M->tri.as<float4>(), M->nnodes, (int)M->nf, brute,
+        M->qout.as<uint8_t>());
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemcpyAsync(vis, M->qout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+}
+
+template <class T> void is_occluded(fluxb200_mesh *M, const int64_t *I, size_t m, const void *D, size_t nd,
+                                    int mode, uint8_t *occ) {
+    FB_REQUIRE(mode >= 0 && mode <= 2, "is_occluded: mode must be 0, 1 or 2");
+    if (mode == 0) FB_REQUIRE(nd == 1, "is_occluded: mode 0 takes one direction");
+    if (mode == 1) FB_REQUIRE(nd == m, "is_occluded: mode 1 needs one direction per face of I");
+    if (!m || !nd) return;
+    cudaStream_t st = M->stream;
+    upload_index_sets(M, I, m, nullptr, 0);
+    const int64_t total = (int64_t)m * (mode == 2 ? (int64_t)nd : 1);
+    M->qout.reserve((size_t)total);
+    M->qtmp.reserve(sizeof(T) * 3 * nd);
+    FB_CUDA(cudaMemcpyAsync(M->qtmp.p, D, sizeof(T) * 3 * nd, cudaMemcpyHostToDevice, st));
+    occluded_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>(
+        M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->qtmp.as<T>(),
+        (int)nd, mode, M->nodes.as<float4>(), M->tri.as<float4>(), M->nnodes, M->qout.as<uint8_t>());
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemcpyAsync(occ, M->qout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+#define DISPATCH(M, fn, ...)                                   \
+    do {                                                       \
+        if ((M)->dtype == FLUXB200_F64) fn<double>(__VA_ARGS__); \
+        else fn<float>(__VA_ARGS__);                           \
+    } while (0)
+
+extern "C" {
+
+const char *fluxb200_last_error(void) { return g_last_error.c_str(); }
+int fluxb200_abi_version(void) { return FLUXB200_ABI_VERSION; }
+
+int fluxb200_device_count(int *count) {
+    return guarded([&] {
+        FB_REQUIRE(count, "count is NULL");
+        FB_CUDA(cudaGetDeviceCount(count));
+    });
+}
+
+int fluxb200_mesh_create(const void *V, size_t nv, const int64_t *F, size_t nf, int dtype_code, int device,
+                         fluxb200_mesh **out) {
+    fluxb200_mesh *M = nullptr;
+    int rc = guarded([&] {
+        FB_REQUIRE(out, "out is NULL");
+        FB_REQUIRE(dtype_code == FLUXB200_F32 || dtype_code == FLUXB200_F64,
+                   "unsupported dtype (float32 and float64 only)");
+        FB_REQUIRE((V || !nv) && (F || !nf), "V / F is NULL");
+        FB_REQUIRE(nf < (1ull << 30) && nv < (1ull << 31), "mesh too large");
+        int ndev = 0;
+        FB_CUDA(cudaGetDeviceCount(&ndev));
+        FB_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+        DeviceGuard guard(device);
+        M = new fluxb200_mesh();
+        M->device = device;
+        M->dtype = dtype_code;
+        M->nv = nv;
+        M->nf = nf;
+        FB_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+        for (auto &e : M->ev) FB_CUDA(cudaEventCreate(&e));
+        FB_CUDA(cudaDeviceGetAttribute(&M->num_sms, cudaDevAttrMultiProcessorCount, device));
+        FB_CUDA(cudaDeviceGetAttribute(&M->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        std::vector<int> F32(3 * nf);
+        for (size_t k = 0; k < 3 * nf; ++k) {
+            if (F[k] < 0 || (size_t)F[k] >= nv) throw CudaError{"F: vertex index out of range"};
+            F32[k] = (int)F[k];
+        }
+        const size_t es = M->esize();
+        M->V.reserve(es * 3 * std::max<size_t>(nv, 1));
+        M->F.reserve(sizeof(int) * 3 * std::max<size_t>(nf, 1));
+        M->V32.reserve(sizeof(float) * 3 * std::max<size_t>(nv, 1));
+        M->faceP.reserve(es * 4 * std::max<size_t>(nf, 1));
+        M->faceN.reserve(es * 4 * std::max<size_t>(nf, 1));
+        if (nv) FB_CUDA(cudaMemcpyAsync(M->V.p, V, es * 3 * nv, cudaMemcpyHostToDevice, M->stream));
+        if (nf) FB_CUDA(cudaMemcpyAsync(M->F.p, F32.data(), sizeof(int) * 3 * nf, cudaMemcpyHostToDevice, M->stream));
+        FB_CUDA(cudaStreamSynchronize(M->stream));
+        DISPATCH(M, build_geometry, M);
+        bvh_build(M);
+        *out = M;
+    });
+    if (rc && M) {
+        fluxb200_mesh_destroy(M);
+    }
+    return rc;
+}
+
+int fluxb200_mesh_destroy(fluxb200_mesh *M) {
+    if (!M) return 0;
+    return guarded([&] {
+        DeviceGuard guard(M->device);
+        if (M->stream) cudaStreamSynchronize(M->stream);
+        DevBuf *bufs[] = {&M->V, &M->F, &M->V32, &M->faceP, &M->faceN, &M->keys, &M->vals, &M->left, &M->right,
+                          &M->parent, &M->first, &M->last, &M->box, &M->flags, &M->pre, &M->flag_by_pre,
+                          &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->rows,
+                          &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
+                          &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
+                          &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};
+        for (DevBuf *b : bufs) b->release();
+        M->sorter.release();
+        for (auto &e : M->ev)
+            if (e) cudaEventDestroy(e);
+        if (M->stream) cudaStreamDestroy(M->stream);
+        delete M;
+    });
+}
+
+int fluxb200_mesh_set_face_data(fluxb200_mesh *M, const void *P, const void *N, const void *A) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        DISPATCH(M, set_face_data, M, P, N, A);
+    });
+}
+
+int fluxb200_mesh_get_face_data(fluxb200_mesh *M, void *P, void *N, void *A) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        DISPATCH(M, get_face_data, M, P, N, A);
+    });
+}
+
+int fluxb200_bvh_build(fluxb200_mesh *M) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        M->have_count = false;
+        bvh_build(M);
+    });
+}
+
+int fluxb200_bvh_info_get(fluxb200_mesh *M, fluxb200_bvh_info *info) {
+    return guarded([&] {
+        FB_REQUIRE(M && info, "NULL argument");
+        info->num_faces = (int64_t)M->nf;
+        info->num_nodes = M->nnodes;
+        info->num_top_nodes = M->ntop;
+        info->max_depth = M->max_depth;
+        info->ms_build = M->ms_build;
+        for (int k = 0; k < 3; ++k) {
+            info->scene_lo[k] = M->scene_h[k];
+            info->scene_hi[k] = M->scene_h[3 + k];
+        }
+    });
+}
+
+int fluxb200_bvh_export(fluxb200_mesh *M, float *nodes, int32_t *leaf_face) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        if (!M->nf) return;
+        if (nodes)
+            FB_CUDA(cudaMemcpyAsync(nodes, M->nodes.p, sizeof(float) * 8 * (size_t)M->nnodes,
+                                    cudaMemcpyDeviceToHost, M->stream));
+        if (leaf_face)
+            FB_CUDA(cudaMemcpyAsync(leaf_face, M->vals.p, sizeof(int32_t) * M->nf, cudaMemcpyDeviceToHost,
+                                    M->stream));
+        FB_CUDA(cudaStreamSynchronize(M->stream));
+    });
+}
+
+int fluxb200_ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n, double eps,
+                      int64_t *row_counts, fluxb200_ff_stats *stats) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        DISPATCH(M, ff_count, M, I, m, J, n, eps, row_counts);
+        if (stats) *stats = M->stats;
+    });
+}
+
+int fluxb200_ff_fill(fluxb200_mesh *M, int index_width, int destination, void *indptr, void *indices,
+                     void *data, fluxb200_ff_stats *stats) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        DISPATCH(M, ff_fill, M, index_width, destination, indptr, indices, data);
+        if (stats) *stats = M->stats;
+    });
+}
+
+int fluxb200_ff_device_csr(fluxb200_mesh *M, void **indptr, void **indices, void **data, int64_t *nnz) {
+    return guarded([&] {
+        FB_REQUIRE(M && M->have_count, "no assembled matrix on this handle");
+        if (indptr) *indptr = M->indptr.p;
+        if (indices) *indices = M->out_indices.p;
+        if (data) *data = M->out_data.p;
+        if (nnz) *nnz = M->nnz;
+    });
+}
+
+int fluxb200_visibility(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                        uint8_t *vis) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        M->have_count = false;
+        DISPATCH(M, visibility, M, I, m, J, n, vis, 0);
+    });
+}
+
+int fluxb200_visibility_bruteforce(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                   uint8_t *vis) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        M->have_count = false;
+        DISPATCH(M, visibility, M, I, m, J, n, vis, 1);
+    });
+}
+
+int fluxb200_is_occluded(fluxb200_mesh *M, const int64_t *I, size_t m, const void *D, size_t nd, int mode,
+                         uint8_t *occluded) {
+    return guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        M->have_count = false;
+        DISPATCH(M, is_occluded, M, I, m, D, nd, mode, occluded);
+    });
+}
+
+int fluxb200_intersect1(fluxb200_mesh *M, const double x[3], const double d[3], int *hit, int64_t *face,
+                        double *t, double xt[3]) {
+    return guarded([&] {
+        FB_REQUIRE(M && x && d && hit, "NULL argument");
+        DeviceGuard guard(M->device);
+        *hit = 0;
+        if (!M->nf) return;
+        M->scalars.reserve(sizeof(int) * 8);
+        int *dface = M->scalars.as<int>() + 4;
+        float *dt = reinterpret_cast<float *>(M->scalars.as<int>() + 5);
+        intersect1_kernel<<<1, 1, 0, M->stream>>>((float)x[0], (float)x[1], (float)x[2], (float)d[0],
+                                                  (float)d[1], (float)d[2], M->nodes.as<float4>(),
+                                                  M->tri.as<float4>(), M->nnodes, dface, dt);
+        FB_CUDA(cudaGetLastError());
+        int hface;
+        float ht;
+        FB_CUDA(cudaMemcpyAsync(&hface, dface, sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+        FB_CUDA(cudaMemcpyAsync(&ht, dt, sizeof(float), cudaMemcpyDeviceToHost, M->stream));
+        FB_CUDA(cudaStreamSynchronize(M->stream));
+        if (hface >= 0) {
+            *hit = 1;
+            if (face) *face = hface;
+            if (t) *t = ht;
+            if (xt)
+                for (int k = 0; k < 3; ++k) xt[k] = x[k] + (double)ht * d[k];
+        }
+    });
+}
+
+int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *starts) {
+    return guarded([&] {
+        FB_REQUIRE(nranks > 0 && starts, "bad arguments");
+        starts[0] = 0;
+        if (!weights) {
+            for (int r = 1; r <= nranks; ++r) starts[r] = (int64_t)(((__int128)m * r) / nranks);
+            return;
+        }
+        long double total = 0;
+        for (size_t k = 0; k < m; ++k) total += (long double)(weights[k] > 0 ? weights[k] : 0) + 1;
+        long double acc = 0;
+        size_t k = 0;
+        for (int r = 1; r < nranks; ++r) {
+            const long double goal = total * r / nranks;
+            while (k < m && acc + (long double)(weights[k] > 0 ? weights[k] : 0) + 1 <= goal) {
+                acc += (long double)(weights[k] > 0 ? weights[k] : 0) + 1;
+                ++k;
+            }
+            starts[r] = (int64_t)k;
+        }
+        starts[nranks] = (int64_t)m;
+    });
+}
+
+int fluxb200_mesh_stream(fluxb200_mesh *M, void **stream) {
+    return guarded([&] {
+        FB_REQUIRE(M && stream, "NULL argument");
+        *stream = (void *)M->stream;
+    });
+}
+
+int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
+    return guarded([&] {
+        FB_REQUIRE(M && name, "NULL argument");
+        DeviceGuard guard(M->device);
+        const std::string s(name);
+        if (s == "top_nodes") {
+            FB_REQUIRE(value >= 0 && value * 32 + 4096 <= M->max_smem_optin, "top_nodes out of range");
+            M->top_nodes_opt = (int)value;
+            M->have_count = false;
+            bvh_build(M);
+        } else if (s == "trace_mode") {
+            FB_REQUIRE(value == 0, "unknown trace_mode");
+            M->trace_mode = (int)value;
+        } else {
+            throw CudaError{"unknown option " + s};
+        }
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,248 @@
+// trace.cuh -- ray set-up, Pluecker triangle test, stackless BVH traversal.
+//
+// Device restatement of the semantics of EmbreeTrimeshShapeModel._get_visibility
+// / _is_occluded (reference src/flux/shape.py:349-421) on Embree's robust-mode
+// closest-hit kernels.  The arithmetic of the ray set-up and of the triangle
+// test is pinned operation by operation (the "arithmetic contract"):
+// every multiply/add goes through a round-to-nearest intrinsic so nvcc cannot
+// contract or reassociate it, fused operations appear only as explicit FMAs.
+// The box test is NOT part of the contract: it only has to be conservative.
+#pragma once
+#include "common.cuh"
+#include "lbvh.cuh"
+
+namespace fluxb200 {
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz;
+};
+
+// 1e3*np.finfo(np.float32).resolution as NumPy 2 evaluates it: float32 0x3A83126F
+__device__ __forceinline__ float ray_eps() { return __uint_as_float(0x3A83126Fu); }
+
+// shape.py:357-362, 380 in float32.  false: pair masked out ("vis by default").
+__device__ __forceinline__ bool setup_ray(const Real4<float> &Pi, const Real4<float> &Pj, Ray &r) {
+    const float eps = ray_eps();
+    const float dx = __fsub_rn(Pj.x, Pi.x), dy = __fsub_rn(Pj.y, Pi.y), dz = __fsub_rn(Pj.z, Pi.z);
+    const float nrm = __fsqrt_rn(
+        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    if (!(nrm > eps)) return false;
+    r.dx = __fdiv_rn(dx, nrm);
+    r.dy = __fdiv_rn(dy, nrm);
+    r.dz = __fdiv_rn(dz, nrm);
+    r.ox = __fadd_rn(Pi.x, __fmul_rn(eps, r.dx));
+    r.oy = __fadd_rn(Pi.y, __fmul_rn(eps, r.dy));
+    r.oz = __fadd_rn(Pi.z, __fmul_rn(eps, r.dz));
+    return true;
+}
+
+// same in float64, rounded to the float32 ray buffers at the end
+__device__ __forceinline__ bool setup_ray(const Real4<double> &Pi, const Real4<double> &Pj, Ray &r) {
+    const double eps = (double)ray_eps();
+    const double dx = __dsub_rn(Pj.x, Pi.x), dy = __dsub_rn(Pj.y, Pi.y), dz = __dsub_rn(Pj.z, Pi.z);
+    const double nrm = __dsqrt_rn(
+        __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    if (!(nrm > eps)) return false;
+    const double Dx = __ddiv_rn(dx, nrm), Dy = __ddiv_rn(dy, nrm), Dz = __ddiv_rn(dz, nrm);
+    r.dx = __double2float_rn(Dx);
+    r.dy = __double2float_rn(Dy);
+    r.dz = __double2float_rn(Dz);
+    r.ox = __double2float_rn(__dadd_rn(Pi.x, __dmul_rn(eps, Dx)));
+    r.oy = __double2float_rn(__dadd_rn(Pi.y, __dmul_rn(eps, Dy)));
+    r.oz = __double2float_rn(__dadd_rn(Pi.z, __dmul_rn(eps, Dz)));
+    return true;
+}
+
+__device__ __forceinline__ float c_msub(float a, float b, float c) { return __fmaf_rn(a, b, -c); }
+__device__ __forceinline__ float c_dot(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, __fmul_rn(az, bz)));
+}
+
+// Embree robust-mode (Pluecker) ray/triangle test; true and t when the ray hits
+// with tnear <= t <= tfar.
+__device__ __forceinline__ bool pluecker_hit(const Ray &r, float tnear, float tfar, const float4 &p0,
+                                             const float4 &p1, const float4 &p2, float &t_out) {
+    const float v0x = __fsub_rn(p0.x, r.ox), v0y = __fsub_rn(p0.y, r.oy), v0z = __fsub_rn(p0.z, r.oz);
+    const float v1x = __fsub_rn(p1.x, r.ox), v1y = __fsub_rn(p1.y, r.oy), v1z = __fsub_rn(p1.z, r.oz);
+    const float v2x = __fsub_rn(p2.x, r.ox), v2y = __fsub_rn(p2.y, r.oy), v2z = __fsub_rn(p2.z, r.oz);
+    const float e0x = __fsub_rn(v2x, v0x), e0y = __fsub_rn(v2y, v0y), e0z = __fsub_rn(v2z, v0z);
+    const float e1x = __fsub_rn(v0x, v1x), e1y = __fsub_rn(v0y, v1y), e1z = __fsub_rn(v0z, v1z);
+    const float e2x = __fsub_rn(v1x, v2x), e2y = __fsub_rn(v1y, v2y), e2z = __fsub_rn(v1z, v2z);
+    float sx, sy, sz, cx, cy, cz;
+    // U = dot(cross(e0, v2+v0), D)
+    sx = __fadd_rn(v2x, v0x); sy = __fadd_rn(v2y, v0y); sz = __fadd_rn(v2z, v0z);
+    cx = c_msub(e0y, sz, __fmul_rn(e0z, sy));
+    cy = c_msub(e0z, sx, __fmul_rn(e0x, sz));
+    cz = c_msub(e0x, sy, __fmul_rn(e0y, sx));
+    const float U = c_dot(cx, cy, cz, r.dx, r.dy, r.dz);
+    sx = __fadd_rn(v0x, v1x); sy = __fadd_rn(v0y, v1y); sz = __fadd_rn(v0z, v1z);
+    cx = c_msub(e1y, sz, __fmul_rn(e1z, sy));
+    cy = c_msub(e1z, sx, __fmul_rn(e1x, sz));
+    cz = c_msub(e1x, sy, __fmul_rn(e1y, sx));
+    const float V = c_dot(cx, cy, cz, r.dx, r.dy, r.dz);
+    sx = __fadd_rn(v1x, v2x); sy = __fadd_rn(v1y, v2y); sz = __fadd_rn(v1z, v2z);
+    cx = c_msub(e2y, sz, __fmul_rn(e2z, sy));
+    cy = c_msub(e2z, sx, __fmul_rn(e2x, sz));
+    cz = c_msub(e2x, sy, __fmul_rn(e2y, sx));
+    const float W = c_dot(cx, cy, cz, r.dx, r.dy, r.dz);
+    const float UVW = __fadd_rn(__fadd_rn(U, V), W);
+    const float eps = __fmul_rn(1.1920929e-7f, fabsf(UVW));
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (!(mn >= -eps || mx <= eps)) return false;
+    // stable triangle normal
+    const float ab_x = __fmul_rn(e0z, e1y), ab_y = __fmul_rn(e0x, e1z), ab_z = __fmul_rn(e0y, e1x);
+    const float bc_x = __fmul_rn(e1z, e2y), bc_y = __fmul_rn(e1x, e2z), bc_z = __fmul_rn(e1y, e2x);
+    const float cabx = c_msub(e0y, e1z, ab_x), caby = c_msub(e0z, e1x, ab_y), cabz = c_msub(e0x, e1y, ab_z);
+    const float cbcx = c_msub(e1y, e2z, bc_x), cbcy = c_msub(e1z, e2x, bc_y), cbcz = c_msub(e1x, e2y, bc_z);
+    const float Ngx = fabsf(ab_x) < fabsf(bc_x) ? cabx : cbcx;
+    const float Ngy = fabsf(ab_y) < fabsf(bc_y) ? caby : cbcy;
+    const float Ngz = fabsf(ab_z) < fabsf(bc_z) ? cabz : cbcz;
+    const float dn = c_dot(Ngx, Ngy, Ngz, r.dx, r.dy, r.dz);
+    const float den = __fadd_rn(dn, dn);
+    const float Tn = c_dot(v0x, v0y, v0z, Ngx, Ngy, Ngz);
+    const float T = __fadd_rn(Tn, Tn);
+    if (den == 0.0f) return false;
+    const float t = __fdiv_rn(T, den);
+    if (!(tnear <= t && t <= tfar)) return false;
+    t_out = t;
+    return true;
+}
+
+// precomputed per-ray data of the (non-contract, conservative) box test
+struct RayBox {
+    float ix, iy, iz; // 1/d with |d| clamped away from zero
+};
+__device__ __forceinline__ RayBox make_raybox(const Ray &r) {
+    auto inv = [](float d) {
+        const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+        return 1.0f / a;
+    };
+    return RayBox{inv(r.dx), inv(r.dy), inv(r.dz)};
+}
+
+// slab test on [0, tmax]; boxes are padded at build time, the comparison has
+// one more relative guard band
+__device__ __forceinline__ bool box_hit(const Ray &r, const RayBox &rb, const float4 &a, const float4 &b,
+                                        float tmax) {
+    const float x0 = (a.x - r.ox) * rb.ix, x1 = (b.x - r.ox) * rb.ix;
+    const float y0 = (a.y - r.oy) * rb.iy, y1 = (b.y - r.oy) * rb.iy;
+    const float z0 = (a.z - r.oz) * rb.iz, z1 = (b.z - r.oz) * rb.iz;
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    return tn <= tf * 1.000001f;
+}
+
+struct BvhView {
+    const float4 *nodes;  // global, 2 float4 per node
+    const float4 *top;    // shared-memory copy of the first ntop nodes (or nullptr)
+    const float4 *tri;    // 3 float4 per triangle, leaf order; tri[3k].w = face id bits
+    int ntop;
+    int nnodes;
+};
+
+__device__ __forceinline__ void load_node(const BvhView &bvh, int node, float4 &a, float4 &b) {
+    if (node < bvh.ntop) {
+        a = bvh.top[2 * node];
+        b = bvh.top[2 * node + 1];
+    } else {
+        a = __ldg(bvh.nodes + 2 * (size_t)node);
+        b = __ldg(bvh.nodes + 2 * (size_t)node + 1);
+    }
+}
+
+// Any triangle k != target that the ray hits with 0 <= t_k and
+// (t_k < tlimit, or t_k == tlimit and face(k) > target_face)?  With
+// tlimit = t of the target triangle this is "closest hit != target" of the
+// oracle's index-ordered closest-hit definition.  tlimit = +inf, target_leaf =
+// -1: plain occlusion query.
+__device__ __forceinline__ bool occluded_anyhit(const BvhView &bvh, const Ray &r, float tlimit,
+                                                int target_leaf, int target_face) {
+    if (bvh.nnodes == 0) return false;
+    const RayBox rb = make_raybox(r);
+    const float tmax = tlimit * 1.000001f;
+    int node = 0;
+    while (node >= 0) {
+        float4 a, b;
+        load_node(bvh, node, a, b);
+        const int skip = __float_as_int(a.w), link = __float_as_int(b.w);
+        if (box_hit(r, rb, a, b, tmax)) {
+            if (link < 0) {
+                const int leaf = ~link;
+                if (leaf != target_leaf) {
+                    const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
+                    const float4 p1 = __ldg(bvh.tri + 3 * (size_t)leaf + 1);
+                    const float4 p2 = __ldg(bvh.tri + 3 * (size_t)leaf + 2);
+                    float t;
+                    if (pluecker_hit(r, 0.0f, tlimit, p0, p1, p2, t)) {
+                        if (t < tlimit || __float_as_int(p0.w) > target_face) return true;
+                    }
+                }
+                node = skip;
+            } else {
+                node = link;
+            }
+        } else {
+            node = skip;
+        }
+    }
+    return false;
+}
+
+// visibility of target triangle (leaf position tleaf, face id tface) along ray r
+__device__ __forceinline__ bool target_visible(const BvhView &bvh, const Ray &r, int tleaf, int tface) {
+    const float4 p0 = __ldg(bvh.tri + 3 * (size_t)tleaf);
+    const float4 p1 = __ldg(bvh.tri + 3 * (size_t)tleaf + 1);
+    const float4 p2 = __ldg(bvh.tri + 3 * (size_t)tleaf + 2);
+    float tj;
+    if (!pluecker_hit(r, 0.0f, __int_as_float(0x7f800000), p0, p1, p2, tj)) return false;
+    return !occluded_anyhit(bvh, r, tj, tleaf, tface);
+}
+
+// the same definitions without the tree (test hook)
+__device__ __forceinline__ bool target_visible_bruteforce(const float4 *tri, int nf, const Ray &r,
+                                                          int tleaf, int tface) {
+    float tj;
+    if (!pluecker_hit(r, 0.0f, __int_as_float(0x7f800000), __ldg(tri + 3 * (size_t)tleaf),
+                      __ldg(tri + 3 * (size_t)tleaf + 1), __ldg(tri + 3 * (size_t)tleaf + 2), tj))
+        return false;
+    for (int k = 0; k < nf; ++k) {
+        if (k == tleaf) continue;
+        const float4 p0 = __ldg(tri + 3 * (size_t)k);
+        float t;
+        if (pluecker_hit(r, 0.0f, tj, p0, __ldg(tri + 3 * (size_t)k + 1), __ldg(tri + 3 * (size_t)k + 2), t))
+            if (t < tj || __float_as_int(p0.w) > tface) return false;
+    }
+    return true;
+}
+
+// closest hit (index-ordered definition) for intersect1
+__device__ __forceinline__ bool closest_hit(const BvhView &bvh, const Ray &r, float &t_best, int &face) {
+    face = -1;
+    if (bvh.nnodes == 0) return false;
+    const RayBox rb = make_raybox(r);
+    int node = 0;
+    while (node >= 0) {
+        float4 a, b;
+        load_node(bvh, node, a, b);
+        const int skip = __float_as_int(a.w), link = __float_as_int(b.w);
+        if (box_hit(r, rb, a, b, t_best * 1.000001f)) {
+            if (link < 0) {
+                const int leaf = ~link;
+                const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
+                float t;
+                if (pluecker_hit(r, 0.0f, t_best, p0, __ldg(bvh.tri + 3 * (size_t)leaf + 1),
+                                 __ldg(bvh.tri + 3 * (size_t)leaf + 2), t)) {
+                    const int f = __float_as_int(p0.w);
+                    if (t < t_best || face < 0 || f > face) {
+                        t_best = t;
+                        face = f;
+                    }
+                }
+                node = skip;
+            } else node = link;
+        } else node = skip;
+    }
+    return face >= 0;
+}
+
+} // namespace fluxb200

@@ -1,0 +1,288 @@
+"""Host-side mirror of ``flux.shape`` for the form-factor path.
+
+Same names, argument meaning and error behaviour as the reference
+(src/flux/shape.py): the geometry helpers (shape.py:16-45), the abstract
+``TrimeshShapeModel`` (shape.py:52-258) with its four backend hooks, and the
+registry list ``trimesh_shape_models`` (shape.py:424-427).  The one backend
+here, ``CudaTrimeshShapeModel``, answers every hook from ``libfluxb200.so``
+(LBVH + stackless traversal on the B200) and adds the fused assembly hook that
+``fluxpy_b200.form_factors.get_form_factor_matrix`` calls once per matrix
+instead of once per row.  No Embree, no CGAL, no CPU fallback.
+"""
+import ctypes
+from abc import ABC
+
+import numpy as np
+
+from . import _lib
+
+
+def get_centroids(V, F):
+    return V[F].mean(axis=1)
+
+
+def get_cross_products(V, F):
+    V0 = V[F[:, 0]]
+    return np.cross(V[F[:, 1]] - V0, V[F[:, 2]] - V0)
+
+
+def get_face_areas(V, F):
+    C = get_cross_products(V, F)
+    return np.sqrt(np.sum(C**2, axis=1))/2
+
+
+def get_surface_normals(V, F):
+    C = get_cross_products(V, F)
+    return C/np.sqrt(np.sum(C**2, axis=1)).reshape(C.shape[0], 1)
+
+
+def get_surface_normals_and_face_areas(V, F):
+    C = get_cross_products(V, F)
+    C_norms = np.sqrt(np.sum(C**2, axis=1))
+    return C/C_norms.reshape(C.shape[0], 1), C_norms/2
+
+
+class ShapeModel(ABC):
+    pass
+
+
+class TrimeshShapeModel(ShapeModel):
+    """A shape model consisting of a single triangle mesh (shape.py:52-258).
+
+    ``V[F]`` yields the faces.  ``N``, ``P``, ``A`` may be passed to override
+    the computed normals / centroids / areas; all three stay public, mutable
+    attributes (the reference tests flip ``N`` in place)."""
+
+    def __init__(self, V, F, N=None, P=None, A=None):
+        if type(self) == TrimeshShapeModel:
+            raise RuntimeError("tried to instantiate TrimeshShapeModel directly")
+        self.dtype = V.dtype
+        self.V = V
+        self.F = F
+        if N is not None and N.shape[0] != F.shape[0]:
+            raise Exception(
+                'must pass same number of surface normals as faces (got ' +
+                '%d faces and %d normals' % (F.shape[0], N.shape[0]))
+        self._make_scene()
+        P0, N0, A0 = self._face_geometry()
+        self.P = P0                      # the reference recomputes P regardless (shape.py:104)
+        self.N = N0 if N is None else N
+        self.A = A0 if A is None else A
+        assert self.P.dtype == self.dtype
+        assert self.N.dtype == self.dtype
+        assert self.A.dtype == self.dtype
+
+    def __reduce__(self):
+        # device state is rebuilt on unpickle, never pickled (shape.py:114-115)
+        return (self.__class__, (self.V, self.F, self.N, self.P, self.A))
+
+    def __repr__(self):
+        return 'a TrimeshShapeModel with %d vertices and %d faces' % (
+            self.num_verts, self.num_faces)
+
+    @property
+    def num_faces(self):
+        return self.P.shape[0]
+
+    @property
+    def num_verts(self):
+        return self.V.shape[0]
+
+    def intersect1(self, x, d):
+        """Trace one ray from `x` along `d`; returns ``(i, xt)`` of the hit or None."""
+        return self._intersect1(x, d)
+
+    def get_visibility(self, I, J, oriented=False):
+        """m x n boolean visibility of centroid-to-centroid rays (shape.py:138-163)."""
+        vis = self._get_visibility(I, J)
+        if oriented:
+            I_, J_ = np.where(vis)
+            gi = np.asarray(I)[I_].astype(np.int64)
+            gj = np.asarray(J)[J_].astype(np.int64)
+            mask = ((self.P[gj] - self.P[gi])*self.N[gi]).sum(1) <= 0
+            vis[I_[mask], J_[mask]] = False
+        return vis
+
+    def get_visibility_1_to_N(self, i, J, oriented=False):
+        return self.get_visibility([i], J, oriented).ravel()
+
+    def get_visibility_matrix(self, oriented=False):
+        I = np.arange(self.num_faces, dtype=np.uintp)
+        return self.get_visibility(I, I, oriented)
+
+    def is_occluded(self, I, D):
+        """Is the ray from each centroid in ``I`` along ``D`` blocked (shape.py:172-179)."""
+        return self._is_occluded(I, D)
+
+    def get_direct_irradiance(self, F0, Dsun, basemesh=None, eps=None):
+        """Insolation for one sun vector, per-face sun vectors or a discretised
+        extended source (shape.py:190-244)."""
+        if basemesh is None:
+            basemesh = self
+        I = ~basemesh.is_occluded(np.arange(self.num_faces), Dsun)
+        if Dsun.ndim == 1:
+            E = np.zeros(self.num_faces, dtype=self.dtype)
+            E[I] = F0*np.maximum(0, self.N[I]@Dsun)
+        elif Dsun.ndim == 2 and Dsun.shape[0] == self.num_faces:
+            if Dsun.shape[1] != 3:
+                raise ValueError('need Dsun.shape[1] == 3 if Dsun.ndim == 2')
+            E = np.zeros(self.num_faces, dtype=self.dtype)
+            E[I] = F0*np.maximum(0, (self.N[I]*Dsun[I]).sum(1))
+        elif Dsun.ndim == 2:
+            if Dsun.shape[1] != 3:
+                raise ValueError('need Dsun.shape[1] == 3 if Dsun.ndim == 2')
+            E = np.where(I, self.N@Dsun.T, 0)
+            E = np.mean(F0)*np.maximum(0, np.sum(E, axis=1)/Dsun.shape[0])
+        else:
+            raise RuntimeError('Dsun.ndim > 2 not implemented yet')
+        return E
+
+
+def _index_array(I):
+    return np.ascontiguousarray(np.asarray(I).astype(np.int64))
+
+
+class CudaTrimeshShapeModel(TrimeshShapeModel):
+    """B200 backend: the four hooks of shape.py:261-292 / 295-421 plus the fused
+    assembly hook, all through the C ABI of ``libfluxb200.so``."""
+
+    device = 0          # CUDA ordinal used by new instances (set per process / rank)
+
+    def _make_scene(self):
+        L = _lib.lib()       # raises if the extension is missing: no fallback
+        self._dtype_code = _lib.dtype_code(self.dtype)
+        V = np.ascontiguousarray(self.V)
+        F = np.ascontiguousarray(self.F, dtype=np.int64)
+        if V.ndim != 2 or V.shape[1] != 3 or F.ndim != 2 or F.shape[1] != 3:
+            raise ValueError('V and F must have shape (*, 3)')
+        h = ctypes.c_void_p()
+        _lib.check(L.fluxb200_mesh_create(_lib.ptr(V), V.shape[0], _lib.ptr(F), F.shape[0],
+                                          self._dtype_code, int(self.device), ctypes.byref(h)))
+        self._handle = h
+        self._nf = F.shape[0]
+
+    def __del__(self):
+        h, self._handle = getattr(self, '_handle', None), None
+        if h and _lib._lib is not None:
+            _lib._lib.fluxb200_mesh_destroy(h)
+
+    def _face_geometry(self):
+        nf = self._nf
+        P = np.empty((nf, 3), self.dtype)
+        N = np.empty((nf, 3), self.dtype)
+        A = np.empty((nf,), self.dtype)
+        _lib.check(_lib.lib().fluxb200_mesh_get_face_data(self._handle, _lib.ptr(P), _lib.ptr(N), _lib.ptr(A)))
+        return P, N, A
+
+    def _sync_face_data(self):
+        """P, N, A are public mutable attributes: refresh the device copies
+        before every query."""
+        arrs = []
+        for a, shape in ((self.P, (self._nf, 3)), (self.N, (self._nf, 3)), (self.A, (self._nf,))):
+            a = np.ascontiguousarray(a)
+            if a.dtype != self.dtype or a.shape != shape:
+                raise RuntimeError(f'face array has dtype/shape {a.dtype}{a.shape}, expected {self.dtype}{shape}')
+            arrs.append(a)
+        _lib.check(_lib.lib().fluxb200_mesh_set_face_data(self._handle, *[_lib.ptr(a) for a in arrs]))
+
+    # ---- hooks ------------------------------------------------------------------
+    def _intersect1(self, x, d):
+        x = np.ascontiguousarray(x, np.float64)
+        d = np.ascontiguousarray(d, np.float64)
+        hit, face, t = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_double(0)
+        xt = np.zeros(3)
+        _lib.check(_lib.lib().fluxb200_intersect1(self._handle, _lib.ptr(x), _lib.ptr(d), ctypes.byref(hit),
+                                                  ctypes.byref(face), ctypes.byref(t), _lib.ptr(xt)))
+        if hit.value:
+            return face.value, xt
+
+    def _get_visibility(self, I, J, _bruteforce=False):
+        I, J = _index_array(I), _index_array(J)
+        self._sync_face_data()
+        vis = np.empty((len(I), len(J)), np.uint8)
+        fn = _lib.lib().fluxb200_visibility_bruteforce if _bruteforce else _lib.lib().fluxb200_visibility
+        _lib.check(fn(self._handle, _lib.ptr(I), len(I), _lib.ptr(J), len(J), _lib.ptr(vis)))
+        vis = vis.astype(bool)
+        # a face does not see itself: the reference's tests expect False on the
+        # diagonal (tests/test_shape.py:37-39, CGAL semantics); the Embree
+        # backend's "masked pair => visible" default is not kept here
+        if len(I) and len(J):
+            vis[I[:, None] == J[None, :]] = False
+        return vis
+
+    def _is_occluded(self, I, D):
+        I = _index_array(I)
+        D = np.ascontiguousarray(D, dtype=self.dtype)
+        if D.ndim != 1 and D.ndim != 2:
+            raise ValueError('D.ndim should be 1 or 2')
+        if D.shape[-1] != 3:
+            raise ValueError('need D.shape[-1] == 3')
+        self._sync_face_data()
+        m = len(I)
+        if D.ndim == 1:
+            mode, nd, shape = 0, 1, (m,)
+        elif D.shape[0] == m:
+            mode, nd, shape = 1, m, (m,)            # one direction per face (Embree backend)
+        else:
+            mode, nd, shape = 2, D.shape[0], (m, D.shape[0])   # CGAL backend's 2-D product
+        occ = np.empty(shape, np.uint8)
+        _lib.check(_lib.lib().fluxb200_is_occluded(self._handle, _lib.ptr(I), m, _lib.ptr(D), nd, mode,
+                                                   _lib.ptr(occ)))
+        return occ.astype(bool)
+
+    # ---- fused assembly hook -------------------------------------------------------
+    def _ff_count(self, I, J, eps, want_row_counts=True):
+        """Pass 1 (cull + trace + count) for rows ``I`` x columns ``J`` (None = all)."""
+        self._sync_face_data()
+        I = None if I is None else _index_array(I)
+        J = None if J is None else _index_array(J)
+        m = self._nf if I is None else len(I)
+        n = self._nf if J is None else len(J)
+        counts = np.empty(m, np.int64) if want_row_counts else None
+        st = _lib.FFStats()
+        _lib.check(_lib.lib().fluxb200_ff_count(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps),
+                                                _lib.ptr(counts), ctypes.byref(st)))
+        self._keep = (I, J)
+        return m, n, counts, st
+
+    def _ff_fill_host(self, m, nnz, index_dtype):
+        """Pass 2 into freshly allocated host arrays."""
+        indptr = np.empty(m + 1, index_dtype)
+        indices = np.empty(nnz, index_dtype)
+        data = np.empty(nnz, self.dtype)
+        st = _lib.FFStats()
+        _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, np.dtype(index_dtype).itemsize, 0,
+                                               _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data),
+                                               ctypes.byref(st)))
+        return indptr, indices, data, st
+
+    def _ff_fill_device(self, index_width=4):
+        """Pass 2 into library-owned device buffers (device-resident CSR)."""
+        st = _lib.FFStats()
+        _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
+        return st
+
+    def bvh_info(self):
+        info = _lib.BvhInfo()
+        _lib.check(_lib.lib().fluxb200_bvh_info_get(self._handle, ctypes.byref(info)))
+        return info
+
+    def bvh_export(self):
+        info = self.bvh_info()
+        nodes = np.zeros((info.num_nodes, 8), np.float32)
+        leaf_face = np.zeros(self._nf, np.int32)
+        _lib.check(_lib.lib().fluxb200_bvh_export(self._handle, _lib.ptr(nodes), _lib.ptr(leaf_face)))
+        return nodes, leaf_face
+
+    def set_option(self, name, value):
+        _lib.check(_lib.lib().fluxb200_set_option(self._handle, name.encode(), int(value)))
+
+    def cuda_stream(self):
+        s = ctypes.c_void_p()
+        _lib.check(_lib.lib().fluxb200_mesh_stream(self._handle, ctypes.byref(s)))
+        return s.value
+
+
+trimesh_shape_models = [
+    CudaTrimeshShapeModel,
+]

@@ -1,0 +1,164 @@
+/*
+ * fluxb200.h -- C ABI of libfluxb200.so, the B200 (sm_100a) implementation of
+ * fluxpy's form-factor assembly hot path.
+ *
+ * Plain C: opaque handle, raw pointers and sizes, int status returns, no
+ * exceptions and no torch / CUDA types cross this boundary.  Every entry point
+ * names the reference interface (relative to the fluxpy source tree) it
+ * replaces.  The shape of the interface mirrors the reference's one existing
+ * native ABI, src/flux/cgal/aabb_wrapper.h:8-16 (opaque struct, alloc / init /
+ * dealloc, batch queries over index arrays).
+ *
+ * Conventions
+ *   - status: 0 = ok, non-zero = failure; fluxb200_last_error() gives the text
+ *     (thread-local, valid until the next call on the same thread).
+ *   - all array arguments are C-contiguous HOST buffers owned by the caller
+ *     unless a parameter is documented as a device pointer.
+ *   - dtype_code: FLUXB200_F32 / FLUXB200_F64 = dtype of V, P, N, A and of the
+ *     returned CSR `data` (shape_model.dtype, src/flux/form_factors.py:32-37).
+ *   - face index arrays I, J are int64, arbitrary order, may repeat; NULL means
+ *     arange(num_faces) (form_factors.py:18-21).
+ *   - calls on one handle are serialised on the handle's own CUDA stream; use
+ *     one handle per device / per host thread.
+ */
+#ifndef FLUXB200_H
+#define FLUXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUXB200_F32 0
+#define FLUXB200_F64 1
+
+#define FLUXB200_ABI_VERSION 1
+
+typedef struct fluxb200_mesh fluxb200_mesh; /* cf. struct cgal_aabb, aabb_wrapper.h:6 */
+
+/* Counters and device timings of the last assembly on a handle. */
+typedef struct fluxb200_ff_stats {
+    int64_t pairs_all;    /* m * n */
+    int64_t pairs_tested; /* pairs surviving the cull form_factors.py:52 (one ray each) */
+    int64_t nnz;          /* stored entries */
+    float ms_prepare;     /* index-set upload, sort of J by leaf order, gathers */
+    float ms_trace;       /* fused cull + occlusion kernel (K4) */
+    float ms_scan;        /* row counts -> indptr (K5) */
+    float ms_fill;        /* order-preserving CSR fill (K6) */
+    float ms_d2h;         /* device -> host copies of the CSR arrays */
+    int32_t trace_launches;
+    int32_t kernel_launches; /* all kernels launched by the last count+fill */
+} fluxb200_ff_stats;
+
+typedef struct fluxb200_bvh_info {
+    int64_t num_faces;
+    int64_t num_nodes;     /* 2*num_faces - 1 */
+    int32_t num_top_nodes; /* nodes staged in shared memory by the trace kernel */
+    int32_t max_depth;
+    float ms_build;        /* device time of the last LBVH build */
+    float scene_lo[3], scene_hi[3];
+} fluxb200_bvh_info;
+
+const char *fluxb200_last_error(void);
+int fluxb200_abi_version(void);
+int fluxb200_device_count(int *count);
+
+/* ---- scene / shape model -------------------------------------------------- */
+
+/* Replaces EmbreeTrimeshShapeModel._make_scene (src/flux/shape.py:296-344) and
+ * cgal_aabb_alloc + cgal_aabb_init_from_trimesh (aabb_wrapper.cpp:36-58):
+ * uploads V (nv x 3, dtype_code) and F (nf x 3 int64), computes centroids,
+ * unit normals and areas on the device in the array dtype with NumPy's
+ * operation order (shape.py:16-45), converts the vertices to the float32
+ * buffer the ray tracer uses (shape.py:319-325) and builds the LBVH. */
+int fluxb200_mesh_create(const void *V, size_t nv, const int64_t *F, size_t nf, int dtype_code,
+                         int device, fluxb200_mesh **out);
+/* cgal_aabb_dealloc (aabb_wrapper.cpp:60-63) */
+int fluxb200_mesh_destroy(fluxb200_mesh *mesh);
+
+/* TrimeshShapeModel keeps P, N, A as mutable public attributes
+ * (shape.py:104-106; the reference tests flip N in place,
+ * tests/test_form_factors.py:33-34,48): the host mirror re-sends them before
+ * every query.  Each pointer may be NULL to keep the device copy.
+ * P, N: nf x 3; A: nf. */
+int fluxb200_mesh_set_face_data(fluxb200_mesh *mesh, const void *P, const void *N, const void *A);
+/* device-computed get_centroids / get_surface_normals_and_face_areas
+ * (shape.py:16-45) back to the host; any pointer may be NULL */
+int fluxb200_mesh_get_face_data(fluxb200_mesh *mesh, void *P, void *N, void *A);
+
+/* Rebuild the LBVH (Morton codes, radix sort, hierarchy, refit, layout).  Done
+ * once by fluxb200_mesh_create; exported so it can be timed. */
+int fluxb200_bvh_build(fluxb200_mesh *mesh);
+int fluxb200_bvh_info_get(fluxb200_mesh *mesh, fluxb200_bvh_info *info);
+/* Debug/test export of the flattened tree: nodes = num_nodes x 8 floats
+ * (lo.xyz, skip-as-int-bits, hi.xyz, link-as-int-bits), leaf_face = nf int32. */
+int fluxb200_bvh_export(fluxb200_mesh *mesh, float *nodes, int32_t *leaf_face);
+
+/* ---- get_form_factor_matrix (src/flux/form_factors.py:11-72) -------------- */
+
+/* Pass 1: per row of I, cull (form_factors.py:46-52), trace the survivors
+ * (shape.py:349-398 semantics) and count the stored entries.
+ * row_counts: int64[m] (host, may be NULL).  The visibility bits stay on the
+ * device for fluxb200_ff_fill; a second count call discards them. */
+int fluxb200_ff_count(fluxb200_mesh *mesh, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                      double eps, int64_t *row_counts, fluxb200_ff_stats *stats);
+/* Pass 2: write the CSR arrays of the last fluxb200_ff_count.
+ * index_width: 4 (int32) or 8 (int64) bytes for indices and indptr.
+ * destination: 0 = host buffers (indptr m+1, indices nnz, data nnz);
+ *              1 = caller-supplied DEVICE buffers of the same sizes;
+ *              2 = library-owned device buffers (see fluxb200_ff_device_csr),
+ *                  the three pointers are ignored.
+ * Columns are positions into J, ascending within each row (form_factors.py:52,69). */
+int fluxb200_ff_fill(fluxb200_mesh *mesh, int index_width, int destination, void *indptr,
+                     void *indices, void *data, fluxb200_ff_stats *stats);
+/* Device pointers of the library-owned CSR of the last destination==2 fill. */
+int fluxb200_ff_device_csr(fluxb200_mesh *mesh, void **indptr, void **indices, void **data,
+                           int64_t *nnz);
+
+/* ---- TrimeshShapeModel hooks (src/flux/shape.py:129-188, 349-421) ---------- */
+
+/* _get_visibility(I, J) -> bool[m, n]: Embree semantics (masked pairs closer
+ * than 1e-3 are visible, otherwise visible iff the closest hit of the ray
+ * p_i -> p_j is triangle j); replaces cgal_aabb_test_face_to_face_vis batched
+ * by AABB.test_face_to_face_vis_MN (src/flux/cgal/aabb.pyx:58-70). */
+int fluxb200_visibility(fluxb200_mesh *mesh, const int64_t *I, size_t m, const int64_t *J,
+                        size_t n, uint8_t *vis);
+/* _is_occluded(I, D): origin P[I] + 1e-3*N[I] (shape.py:400-421).
+ * mode 0: D is one vector (3), out[m];
+ * mode 1: D is m x 3, row p belongs to I[p], out[m]        (Embree backend);
+ * mode 2: D is nd x 3, all directions for every face, out[m x nd]
+ *         (ray_from_centroid_is_occluded_2d, aabb.pyx:77-87). */
+int fluxb200_is_occluded(fluxb200_mesh *mesh, const int64_t *I, size_t m, const void *D, size_t nd,
+                         int mode, uint8_t *occluded);
+/* _intersect1(x, d): closest hit of one ray (double in, as cgal_aabb_intersect1,
+ * aabb_wrapper.cpp:109-129).  *hit = 1 and face / t / xt filled when something is hit. */
+int fluxb200_intersect1(fluxb200_mesh *mesh, const double x[3], const double d[3], int *hit,
+                        int64_t *face, double *t, double xt[3]);
+
+/* ---- test hooks ------------------------------------------------------------ */
+
+/* Same as fluxb200_visibility but every ray is tested against every triangle
+ * (no BVH): validates the tree and the conservative box test on the device. */
+int fluxb200_visibility_bruteforce(fluxb200_mesh *mesh, const int64_t *I, size_t m,
+                                   const int64_t *J, size_t n, uint8_t *vis);
+
+/* ---- multi-GPU helpers ----------------------------------------------------- */
+
+/* Contiguous row slabs for `nranks` devices (rows shard):
+ * starts[nranks+1].  weights (int64[m], e.g. row counts of a previous pass) may
+ * be NULL for an equal split. */
+int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *starts);
+
+/* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, so a
+ * caller can bracket calls with its own events. */
+int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
+/* Tunables: "top_nodes" (BVH nodes staged in shared memory), "trace_mode"
+ * (0 = per-ray stackless, 1 = warp-packet stackless), "rows_per_launch". */
+int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUXB200_H */

@@ -1,0 +1,273 @@
+"""GPU tier: the CUDA path (through the C ABI, via the host mirror of the
+reference's interface) against the CPU oracle on the same inputs and against
+the golden vectors produced by the reference's own Python.
+
+Bars: visibility bits, CSR pattern and ray set-up bit-exact against the oracle;
+F_ij bit-exact against the oracle (same arithmetic contract) and within 1e-5
+(float32) / 1e-12 (float64) relative of the float64 ground truth; steady-state
+temperature within 1e-6 relative L2 of the reference's."""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float64, np.float32]
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import fluxpy_b200
+    from fluxpy_b200 import meshes, shape, form_factors
+    from oracle import oracle, radiosity
+    return dict(pkg=fluxpy_b200, meshes=meshes, shape=shape, ff=form_factors, oracle=oracle,
+                radiosity=radiosity)
+
+
+def same_csr(A, B):
+    A.sort_indices()
+    B.sort_indices()
+    return (A.shape == B.shape and np.array_equal(A.indptr, B.indptr)
+            and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data))
+
+
+def test_library_loaded_and_device_present(mods):
+    from fluxpy_b200 import _lib
+    assert _lib.device_count() >= 1
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('name', ['icosa_sphere', 'icosa_sphere_5'])
+def test_sphere_fixtures(mods, name, dtype, digests):
+    """reference tests/test_form_factors.py:18-57 + golden values."""
+    g = helpers.load(name)
+    V, F = g['V'].astype(dtype), g['F']
+    for Model in mods['shape'].trimesh_shape_models:
+        sm = Model(V, F)
+        om = mods['oracle'].OracleShapeModel(V, F)
+        assert np.array_equal(sm.P, om.P) and np.array_equal(sm.N, om.N) and np.array_equal(sm.A, om.A)
+        outward = (sm.P*sm.N).sum(1) > 0
+        sm.N[outward] *= -1
+        om.N[outward] *= -1
+        FF = mods['ff'].get_form_factor_matrix(sm)
+        nf = len(F)
+        assert FF.dtype == dtype and FF.shape == (nf, nf) and FF.nnz == nf*(nf - 1)
+        assert FF.indices.dtype == np.int32 and FF.indptr.dtype == np.int32 and FF.has_sorted_indices
+        D = FF.toarray()
+        assert (np.diag(D) == 0).all() and ((D != 0) | np.eye(nf, dtype=bool)).all()
+        assert same_csr(FF, mods['oracle'].get_form_factor_matrix(om))
+        tag = np.dtype(dtype).name
+        dg = digests[f'{name}/inward/{tag}']
+        ref = g[f'inward_{tag}_data']
+        rtol = 2e-5 if dtype == np.float32 else 1e-12
+        assert np.allclose(FF.data, ref, rtol=rtol, atol=0)
+        assert abs(FF.data.astype(np.float64).sum() - dg['sum']) <= 1e-6*dg['sum']
+        sm.N *= -1
+        FFo = mods['ff'].get_form_factor_matrix(sm)
+        assert FFo.nnz == 0 and (FFo.toarray() == 0).all()
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_sphere_shape_api(mods, dtype):
+    """reference tests/test_shape.py:16-112 on the CUDA backend."""
+    g = helpers.load('icosa_sphere')
+    V, F = g['V'].astype(dtype), g['F']
+    for Model in mods['shape'].trimesh_shape_models:
+        sm = Model(V, F)
+        sm.N[(sm.N*sm.P).sum(1) < 0] *= -1
+        nf = sm.num_faces
+        off = ~np.eye(nf, dtype=bool)
+        assert (sm.get_visibility_matrix(oriented=False) == off).all()
+        assert not sm.get_visibility_matrix(oriented=True).any()
+        sm.N *= -1
+        vis = sm.get_visibility_matrix(oriented=False)
+        assert (vis == off).all()
+        assert (sm.get_visibility_matrix(oriented=True) == off).all()
+        I = np.arange(nf)
+        for i in (0, 13, nf - 1):
+            assert (sm.get_visibility_1_to_N(i, I) == vis[i]).all()
+        sm.N *= -1
+        tag = np.dtype(dtype).name
+        D = g[f'occ_D_{tag}']
+        occ = sm.is_occluded(np.arange(nf), D)
+        assert (np.packbits(occ) == g[f'occ_{tag}']).all()
+        clear = abs(sm.N@D) > 0.05
+        assert (occ == (sm.N@D < 0))[clear].all()
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+@pytest.mark.parametrize('case', [(16, 0), (24, 1), (40, 2)])
+def test_crater_vs_oracle_and_golden(mods, case, dtype, digests):
+    n, seed = case
+    name = f'crater_n{n}_s{seed}'
+    tag = np.dtype(dtype).name
+    g = helpers.load(name)
+    V, F = mods['meshes'].gaussian_crater(n, seed, dtype=dtype)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    nf = sm.num_faces
+    # visibility: BVH == brute force on the device == oracle == reference golden
+    vis = sm._get_visibility(np.arange(nf), np.arange(nf))
+    visb = sm._get_visibility(np.arange(nf), np.arange(nf), _bruteforce=True)
+    assert (vis == visb).all()
+    vo = om.get_visibility_matrix()
+    eye = np.eye(nf, dtype=bool)
+    assert (vis == (vo & ~eye)).all()
+    assert helpers.sha(np.packbits(vis | eye)) == digests[f'{name}/vis/{tag}']['sha256']
+    # sun occlusion
+    occ = sm.is_occluded(np.arange(nf), g[f'Dsun_{tag}'])
+    assert (np.packbits(occ) == g[f'occ_{tag}']).all()
+    # form factors, full matrix: bit-exact against the oracle
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    st = dict(mods['ff'].last_stats)
+    FO, so = mods['oracle'].get_form_factor_matrix(om, return_stats=True)
+    assert same_csr(FF, FO)
+    assert st['pairs_tested'] == so['pairs_tested'] and st['nnz'] == so['nnz'] == FF.nnz
+    assert st['pairs_all'] == nf*nf
+    dg = digests[f'{name}/full/{tag}']
+    if dtype == np.float64:
+        assert FF.nnz == dg['nnz'] and helpers.sha(FF.indices.astype(np.int64)) == dg['indices_sha256']
+        assert helpers.sha(FF.indptr.astype(np.int64)) == dg['indptr_sha256']
+    I = np.arange(nf)
+    if f'indptr_{tag}' in g:
+        helpers.check_against_reference_csr(FF, g[f'indptr_{tag}'], g[f'indices_{tag}'], g[f'data_{tag}'],
+                                            sm.P, sm.N, sm.A, I, I, 1e-5, dtype)
+    # per-block assembly with arbitrary index sets (compressed_form_factors.py:556-560)
+    Ib, Jb = g[f'I_{tag}'].astype(np.int64), g[f'J_{tag}'].astype(np.int64)
+    FB = mods['ff'].get_form_factor_matrix(sm, Ib, Jb)
+    assert same_csr(FB, mods['oracle'].get_form_factor_matrix(om, Ib, Jb))
+    S = FF[Ib, :][:, Jb]
+    S.sort_indices()
+    assert np.array_equal(S.indices, FB.indices) and np.array_equal(S.data, FB.data)
+    if f'block_indptr_{tag}' in g:
+        helpers.check_against_reference_csr(FB, g[f'block_indptr_{tag}'], g[f'block_indices_{tag}'],
+                                            g[f'block_data_{tag}'], sm.P, sm.N, sm.A, Ib, Jb, 1e-5, dtype)
+
+
+@pytest.mark.parametrize('dtype', DTYPES)
+def test_steady_state_temperature(mods, dtype):
+    """north_star: steady-state thermal solution within 1e-6 relative L2 of the
+    reference's (model.py:8-24 run by oracle/make_golden.py)."""
+    tag = np.dtype(dtype).name
+    g = helpers.load('crater_n24_s1')
+    V, F = mods['meshes'].gaussian_crater(24, 1, dtype=dtype)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    E = sm.get_direct_irradiance(1365.0, g[f'Dsun_{tag}'])
+    assert np.allclose(E, g[f'E_{tag}'], rtol=1e-6, atol=1e-4)
+    T = mods['radiosity'].compute_steady_state_temp(FF, E.astype(np.float64), 0.12, 0.95)
+    Tref = g[f'T_{tag}']
+    assert np.linalg.norm(T - Tref) <= 1e-6*np.linalg.norm(Tref)
+
+
+def test_edge_cases(mods):
+    V, F = mods['meshes'].gaussian_crater(16, 0, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    gf = mods['ff'].get_form_factor_matrix
+    e = np.array([], dtype=np.uintp)
+    assert gf(sm, e, np.arange(10)).shape == (0, 10)
+    FF = gf(sm, np.arange(10), e)
+    assert FF.shape == (10, 0) and FF.nnz == 0
+    # duplicates / unsorted J, single row, single column
+    J = np.array([5, 400, 5, 7, 449, 0])
+    assert same_csr(gf(sm, [100], J), mods['oracle'].get_form_factor_matrix(om, [100], J))
+    assert same_csr(gf(sm, np.arange(450), [17]), mods['oracle'].get_form_factor_matrix(om, np.arange(450), [17]))
+    # negative eps keeps everything incl. the (zero) diagonal and masked pairs
+    assert same_csr(gf(sm, eps=-1.0), mods['oracle'].get_form_factor_matrix(om, eps=-1.0))
+    # huge eps culls everything
+    assert gf(sm, eps=1e9).nnz == 0
+    # errors: bad index, bad dtype, direct instantiation (shape.py:84-85)
+    with pytest.raises(RuntimeError):
+        gf(sm, [0], [10**6])
+    with pytest.raises(RuntimeError):
+        mods['shape'].CudaTrimeshShapeModel(V.astype(np.float16), F)
+    with pytest.raises(RuntimeError):
+        mods['shape'].TrimeshShapeModel(V, F)
+    # pickling rebuilds the device scene (shape.py:114-115)
+    import pickle
+    sm2 = pickle.loads(pickle.dumps(sm))
+    assert same_csr(gf(sm2), gf(sm))
+    # intersect1: straight down onto the crater floor
+    hit = sm.intersect1(np.array([0.01, 0.02, 1.0]), np.array([0, 0, -1.0]))
+    assert hit is not None and abs(hit[1][2] - (-0.4)) < 0.1
+
+
+def test_bvh_structure(mods):
+    """Every leaf triangle lies inside all its ancestors' boxes; skip links walk
+    the whole tree exactly once."""
+    V, F = mods['meshes'].gaussian_crater(40, 2, dtype=np.float32)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F)
+    nodes, leaf_face = sm.bvh_export()
+    nf = sm.num_faces
+    assert sorted(leaf_face.tolist()) == list(range(nf))
+    skip = nodes[:, 3].view(np.int32)
+    link = nodes[:, 7].view(np.int32)
+    # full traversal: always descend
+    seen, node, leaves = 0, 0, []
+    while node >= 0:
+        seen += 1
+        if link[node] < 0:
+            leaves.append(~link[node])
+            node = skip[node]
+        else:
+            node = link[node]
+    assert seen == 2*nf - 1 and sorted(leaves) == list(range(nf))
+    # containment of each triangle in its leaf box and in the root box
+    tri = V[F[leaf_face]]                       # (nf, 3, 3) in leaf order
+    leaf_nodes = np.where(link < 0)[0]
+    order = ~link[leaf_nodes]
+    lo, hi = nodes[leaf_nodes, 0:3], nodes[leaf_nodes, 4:7]
+    t = tri[order]
+    assert (t.min(1) >= lo).all() and (t.max(1) <= hi).all()
+    assert (V.min(0) >= nodes[0, 0:3]).all() and (V.max(0) <= nodes[0, 4:7]).all()
+    info = sm.bvh_info()
+    assert info.num_nodes == 2*nf - 1 and 0 < info.num_top_nodes <= 1024
+
+
+@pytest.mark.parametrize('dtype', [np.float32])
+def test_crater_10k_vs_oracle(mods, dtype):
+    """BASELINE config 5, smallest size: G(72, 0), 10 082 faces, 1.0e8 pairs."""
+    V, F = mods['meshes'].gaussian_crater(72, 0, dtype=dtype)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    FO = mods['oracle'].get_form_factor_matrix(om)
+    assert same_csr(FF, FO)
+    rs = np.asarray(FF.sum(axis=1)).ravel()
+    assert rs.max() < 1.0 and FF.nnz > 0.3*FF.shape[0]**2
+
+
+def test_slab_properties_at_full_size(mods):
+    """BASELINE config 3 size (G(317, 0), 199 712 faces): properties that do not
+    need the oracle.  A slab of rows equals the same rows assembled in another
+    slab split; reciprocity A_i F_ij == A_j F_ji on a symmetric sub-block;
+    columns ascending; oracle agreement on a few sampled rows."""
+    V, F = mods['meshes'].gaussian_crater(317, 0, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    gf = mods['ff'].get_form_factor_matrix
+    nf = sm.num_faces
+    rows = np.arange(1000, 1256)
+    A = gf(sm, rows)
+    B1, B2 = gf(sm, rows[:100]), gf(sm, rows[100:])
+    import scipy.sparse
+    assert same_csr(A, scipy.sparse.vstack([B1, B2]).tocsr())
+    for r in range(A.shape[0]):
+        c = A.indices[A.indptr[r]:A.indptr[r + 1]]
+        assert (np.diff(c) > 0).all()
+    # reciprocity on a symmetric block
+    S = np.arange(50000, 50512)
+    Q = gf(sm, S, S).toarray().astype(np.float64)
+    a = sm.A[S].astype(np.float64)
+    both = (Q > 0) & (Q.T > 0)
+    lhs, rhs = a[:, None]*Q, (a[:, None]*Q).T
+    assert np.allclose(lhs[both], rhs[both], rtol=1e-5, atol=0)
+    # sampled rows against the oracle at full size
+    om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    samp = np.array([0, 77777, 150001, nf - 1])
+    assert same_csr(gf(sm, samp), mods['oracle'].get_form_factor_matrix(om, samp))

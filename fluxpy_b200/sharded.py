@@ -1,0 +1,91 @@
+"""Row-sharded assembly over the GPUs of one box.
+
+Rows of F are independent (reference src/flux/form_factors.py:45-70 carries no
+cross-row state except the running ``indptr`` sum, :54, :70), so the mesh and
+its LBVH are replicated on every GPU, each rank assembles one contiguous slab
+of ``I`` and the ONLY exchange is an all-gather of the per-row counts, from
+which every rank derives the global ``indptr`` and the offset of its slab.
+``data`` / ``indices`` never cross GPUs.
+
+One process per GPU, ``torch.distributed`` as plumbing (NCCL over NVLink on
+the box, gloo in the CPU tests).
+"""
+import numpy as np
+
+from . import _lib, config
+
+
+def slab_bounds(m, world_size, weights=None):
+    """``starts[world_size+1]`` of the contiguous row slabs (C ABI:
+    ``fluxb200_slab_plan``); ``weights`` (e.g. row counts of an earlier pass)
+    balances by work instead of by rows."""
+    return _lib.slab_plan(m, world_size, weights)
+
+
+def exchange_row_counts(local_counts, starts, group=None, device=None):
+    """All-gather the per-row counts of every slab -> global int64 ``indptr``
+    (length m+1) on every rank.  ``local_counts``: int64[rows of my slab]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = np.diff(starts).astype(np.int64)
+    assert len(sizes) == world and len(local_counts) == sizes[rank]
+    width = int(sizes.max()) if world else 0
+    dev = device if device is not None else 'cpu'
+    mine = torch.zeros(max(width, 1), dtype=torch.int64, device=dev)
+    if sizes[rank]:
+        mine[:sizes[rank]] = torch.as_tensor(np.asarray(local_counts, np.int64), device=dev)
+    gathered = torch.empty(world*max(width, 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    g = gathered.cpu().numpy().reshape(world, max(width, 1))
+    counts = np.concatenate([g[r, :sizes[r]] for r in range(world)]) if world else np.zeros(0, np.int64)
+    indptr = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    return indptr
+
+
+class SlabResult:
+    """What one rank holds after a sharded assembly."""
+
+    def __init__(self, row_start, row_stop, global_indptr, local_csr, stats):
+        self.row_start, self.row_stop = int(row_start), int(row_stop)
+        self.global_indptr = global_indptr
+        self.local_csr = local_csr       # scipy CSR of my rows (None in device-resident mode)
+        self.stats = stats
+
+    @property
+    def nnz_offset(self):
+        return int(self.global_indptr[self.row_start])
+
+
+def get_form_factor_matrix_sharded(shape_model, I=None, J=None, eps=None, group=None,
+                                   to_host=True, weights=None):
+    """Every rank calls this with the same arguments and its own
+    ``CudaTrimeshShapeModel`` (same mesh, its own device).  Returns this rank's
+    :class:`SlabResult`; the full matrix is the vertical stack of the slabs in
+    rank order."""
+    import scipy.sparse
+    import torch.distributed as dist
+    if eps is None:
+        eps = config.DEFAULT_EPS
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nf = shape_model.num_faces
+    I = np.arange(nf, dtype=np.int64) if I is None else np.asarray(I).astype(np.int64)
+    starts = slab_bounds(len(I), world, weights)
+    lo, hi = int(starts[rank]), int(starts[rank + 1])
+    m, n, counts, st = shape_model._ff_count(I[lo:hi], J, eps, want_row_counts=True)
+    dev = None
+    if dist.get_backend(group) == 'nccl':
+        import torch
+        dev = torch.device('cuda', shape_model.device)
+    indptr = exchange_row_counts(counts, starts, group, dev)
+    local = None
+    if to_host:
+        nnz = int(st.nnz)
+        idt = np.int32 if max(nnz, n, m + 1) < 2**31 else np.int64
+        ip, ix, dv, st = shape_model._ff_fill_host(m, nnz, idt)
+        local = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n), copy=False)
+    else:
+        st = shape_model._ff_fill_device(4 if max(int(st.nnz), n) < 2**31 else 8)
+    return SlabResult(lo, hi, indptr, local, st.as_dict())

@@ -1,0 +1,139 @@
+"""CPU tier: C-ABI surface, host-side logic, multi-rank row-count exchange (gloo)."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from fluxpy_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'fluxb200.h')).read()
+    declared = set(re.findall(r'\b(fluxb200_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().fluxb200_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_oracle_in_product_path():
+    """The shipped package never imports, links or executes the oracle."""
+    pkg = os.path.join(ROOT, 'fluxpy_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')) or f == 'Makefile':
+                txt = open(os.path.join(dirpath, f)).read()
+                for needle in ('import oracle', 'from oracle', 'ff_oracle', 'oracle/', 'oracle.'):
+                    assert needle not in txt, (f, needle)
+
+
+def test_missing_device_fails_loudly():
+    """No CUDA device in the build container: constructing a shape model must
+    raise, not fall back to a CPU path."""
+    from fluxpy_b200 import _lib, meshes, shape
+    try:
+        n = _lib.device_count()
+    except RuntimeError:
+        n = 0
+    if n:
+        pytest.skip('a GPU is present')
+    V, F = meshes.gaussian_crater(8, 0)
+    with pytest.raises(RuntimeError):
+        shape.CudaTrimeshShapeModel(V, F)
+    from fluxpy_b200.form_factors import get_form_factor_matrix
+
+    class Fake:
+        dtype = np.dtype(np.float32)
+    with pytest.raises(RuntimeError):
+        get_form_factor_matrix(Fake())
+
+
+def test_slab_plan():
+    from fluxpy_b200 import _lib
+    assert _lib.slab_plan(10, 3).tolist() == [0, 3, 6, 10]
+    assert _lib.slab_plan(0, 4).tolist() == [0, 0, 0, 0, 0]
+    assert _lib.slab_plan(3, 8).tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 3]
+    s = _lib.slab_plan(1000, 8, np.r_[np.zeros(900), np.full(100, 1000)])
+    assert s[0] == 0 and s[-1] == 1000 and (np.diff(s) >= 0).all() and s[1] >= 900
+    w = np.random.default_rng(0).integers(0, 100, 5000)
+    s = _lib.slab_plan(5000, 8, w)
+    loads = [w[s[k]:s[k + 1]].sum() for k in range(8)]
+    assert max(loads) < 1.1*np.mean(loads)
+
+
+def test_geometry_helpers_match_reference_formulas():
+    from fluxpy_b200 import meshes, shape
+    V, F = meshes.gaussian_crater(12, 3, dtype=np.float64)
+    N, A = shape.get_surface_normals_and_face_areas(V, F)
+    assert np.allclose(np.linalg.norm(N, axis=1), 1) and (N[:, 2] > 0).all()
+    assert np.isclose(A.sum(), shape.get_face_areas(V, F).sum())
+    assert np.allclose(shape.get_centroids(V, F), V[F].mean(1))
+    assert meshes.gaussian_crater(72)[1].shape[0] == 10082
+    assert meshes.grid_faces(159).shape[0] == 49928 and meshes.grid_faces(317).shape[0] == 199712
+    Vs, Fs = meshes.icosphere(2)
+    assert Fs.shape[0] == 320 and np.allclose(np.linalg.norm(Vs, axis=1), 1)
+    Ns = shape.get_surface_normals(Vs, Fs)
+    assert ((Ns*shape.get_centroids(Vs, Fs)).sum(1) > 0).all()
+
+
+def test_block_index_sets_match_reference_golden():
+    """get_quadrant_order / get_octant_order (quadtree.py:5-18, octree.py:5-18)."""
+    from fluxpy_b200 import blocks
+    from tests import helpers
+    g = helpers.load('block_inds')
+    P = g['P']
+    for k, I in enumerate(blocks.get_quadrant_order(P[:, :2])):
+        assert np.array_equal(I, g[f'quad{k}'])
+    for k, I in enumerate(blocks.get_octant_order(P)):
+        assert np.array_equal(I, g[f'oct{k}'])
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fluxpy_b200 import sharded
+dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{sys.argv[2]}',
+                        rank=int(sys.argv[3]), world_size=int(sys.argv[4]))
+rank, world = dist.get_rank(), dist.get_world_size()
+m = 37
+rng = np.random.default_rng(5)
+counts = rng.integers(0, 1000, m).astype(np.int64)      # what a 1-GPU pass would count
+starts = sharded.slab_bounds(m, world)
+mine = counts[starts[rank]:starts[rank + 1]]
+indptr = sharded.exchange_row_counts(mine, starts)
+expect = np.r_[0, np.cumsum(counts)]
+assert np.array_equal(indptr, expect), (indptr, expect)
+# weighted plan agrees on every rank and covers all rows
+s2 = sharded.slab_bounds(m, world, counts)
+assert s2[0] == 0 and s2[-1] == m
+indptr2 = sharded.exchange_row_counts(counts[s2[rank]:s2[rank + 1]], s2)
+assert np.array_equal(indptr2, expect)
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_row_count_exchange_gloo(world, tmp_path):
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / 'worker.py'
+    script.write_text(_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), str(world)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -218,12 +218,11 @@ def main():
         rows = slab_rows(s, rank, world, args.rows, nf)
         with torch.cuda.stream(stream):
             flush.zero_()                       # L2 flush between steps (in-stream, ~0.1 ms)
-        m, n, counts, st = sm._ff_count(rows, None, EPS, want_row_counts=True)
+        m, n, counts, st = sm._ff_assemble_device(rows, None, EPS, 4, want_row_counts=world > 1)
         if world > 1:                           # C1: all-gather of the slab's row counts
             starts = np.arange(world + 1, dtype=np.int64)*len(rows)
             sharded.exchange_row_counts(counts, starts, None, dev)
-        st2 = sm._ff_fill_device(4)
-        return st, st2
+        return st, st
 
     for s in range(args.warmup):
         step_device(s)
@@ -232,7 +231,8 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    acc = {'tested': 0, 'pairs': 0, 'nnz': 0, 'trace_ms': 0.0, 'fill_ms': 0.0, 'launches': 0, 'rows': 0}
+    acc = {'tested': 0, 'pairs': 0, 'nnz': 0, 'trace_ms': 0.0, 'fill_ms': 0.0, 'launches': 0, 'rows': 0,
+           'trace_launches': 0}
     for s in range(args.warmup, args.warmup + args.steps):
         st, st2 = step_device(s)
         acc['tested'] += st.pairs_tested
@@ -240,6 +240,7 @@ def main():
         acc['nnz'] += st.nnz
         acc['trace_ms'] += st.ms_trace
         acc['fill_ms'] += st2.ms_fill
+        acc['trace_launches'] += st.trace_launches
         acc['launches'] += st2.kernel_launches + 1      # + the L2-flush memset
         acc['rows'] += len(slab_rows(s, rank, world, args.rows, nf))
     e1.record(stream)
@@ -300,9 +301,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
         full = slab_rows(args.warmup, 0, 1, args.rows, nf)
-        probe = full[np.linspace(0, len(full) - 1, 4).astype(int)]
+        probe = full[np.linspace(0, len(full) - 1, 2*cores).astype(int)]
         t, p, dt = cpu_port_sample(V, F, N, probe)
-        nrows = args.cpu_rows or int(min(len(full), max(8, round(15.0/(dt/len(probe))))))
+        nrows = args.cpu_rows or int(min(len(full), max(2*cores, round(15.0/(dt/len(probe))))))
         rows = full[np.linspace(0, len(full) - 1, nrows).astype(int)]
         t, p, dt = cpu_port_sample(V, F, N, rows)
         cpu = {'value': t/dt, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
@@ -316,15 +317,16 @@ def main():
         fp32_peak = props.multi_processor_count*128*2*sm_max_mhz*1e6/1e12       # TFLOP/s
         # dominant kernel = trace_kernel (one launch per step per rank); per-launch figures of rank 0
         steps = args.steps
-        fl = alg_flops(acc['pairs'], acc['tested'], 0, nf)/steps                   # trace part
-        trace_s = acc['trace_ms']/steps/1e3
+        nl = max(1, acc['trace_launches'])
+        fl = alg_flops(acc['pairs'], acc['tested'], 0, nf)/nl                      # per trace launch
+        trace_s = acc['trace_ms']/nl/1e3
         by = alg_bytes(acc['nnz']/steps, acc['rows']/steps, nf)
         assemble_s = ms_dev/steps/1e3
         roof = {
             'kernel': 'trace_kernel<float> (fused cull + occlusion traversal)',
             'bound': 'fp32', 'achieved': fl/trace_s/1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
             'frac': fl/trace_s/1e12/fp32_peak, 'traffic': None, 'peak_source': 'SMs*128*2*sm_max_mhz',
-            'alg_flop_per_launch': fl, 'launch_ms': 1e3*trace_s,
+            'alg_flop_per_launch': fl, 'launch_ms': 1e3*trace_s, 'launches_per_step': nl/steps,
             'hbm': {'bound': 'hbm', 'achieved': by/assemble_s/1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': by/assemble_s/1e9/hbm_peak, 'alg_bytes_per_step': by, 'peak_source': peak_src},
             'trace_share_of_step': acc['trace_ms']/ms_dev,

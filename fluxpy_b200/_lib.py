@@ -15,14 +15,16 @@ SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+OVERFLOW = 2
 
 #: every symbol include/fluxb200.h declares
 EXPORTS = (
     'fluxb200_last_error', 'fluxb200_abi_version', 'fluxb200_device_count',
     'fluxb200_mesh_create', 'fluxb200_mesh_destroy', 'fluxb200_mesh_set_face_data',
     'fluxb200_mesh_get_face_data', 'fluxb200_bvh_build', 'fluxb200_bvh_info_get',
-    'fluxb200_bvh_export', 'fluxb200_ff_count', 'fluxb200_ff_fill', 'fluxb200_ff_device_csr',
+    'fluxb200_bvh_export', 'fluxb200_ff_count', 'fluxb200_ff_fill', 'fluxb200_ff_assemble',
+    'fluxb200_host_alloc', 'fluxb200_host_free', 'fluxb200_ff_device_csr',
     'fluxb200_visibility', 'fluxb200_is_occluded', 'fluxb200_intersect1',
     'fluxb200_visibility_bruteforce', 'fluxb200_slab_plan', 'fluxb200_mesh_stream',
     'fluxb200_set_option',
@@ -89,6 +91,10 @@ def lib():
     L.fluxb200_bvh_export.argtypes = [vp, vp, vp]
     L.fluxb200_ff_count.argtypes = [vp, vp, sz, vp, sz, ctypes.c_double, vp, ctypes.POINTER(FFStats)]
     L.fluxb200_ff_fill.argtypes = [vp, i32, i32, vp, vp, vp, ctypes.POINTER(FFStats)]
+    L.fluxb200_ff_assemble.argtypes = [vp, vp, sz, vp, sz, ctypes.c_double, i32, i32, vp, vp, vp, i64, vp,
+                                       ctypes.POINTER(FFStats)]
+    L.fluxb200_host_alloc.argtypes = [sz, pp]
+    L.fluxb200_host_free.argtypes = [vp]
     L.fluxb200_ff_device_csr.argtypes = [vp, pp, pp, pp, ctypes.POINTER(i64)]
     L.fluxb200_visibility.argtypes = [vp, vp, sz, vp, sz, vp]
     L.fluxb200_visibility_bruteforce.argtypes = [vp, vp, sz, vp, sz, vp]
@@ -137,3 +143,77 @@ def slab_plan(m, nranks, weights=None):
     w = None if weights is None else np.ascontiguousarray(weights, np.int64)
     check(lib().fluxb200_slab_plan(int(m), int(nranks), ptr(w), ptr(starts)))
     return starts
+
+
+# ---------------------------------------------------------------------------
+# page-locked host arena for the CSR outputs
+# ---------------------------------------------------------------------------
+class _Block:
+    __slots__ = ('ptr', 'nbytes', 'leases')
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes, self.leases = ptr, nbytes, 0
+
+
+class _Lease:
+    """Exposes a slice of a pinned block to NumPy (``__array_interface__``); the
+    arrays made from it keep it alive, and when the last one dies the block goes
+    back to the arena."""
+
+    def __init__(self, arena, block, offset, count, dtype):
+        self._arena, self._block = arena, block
+        block.leases += 1
+        self.__array_interface__ = {'shape': (int(count),), 'typestr': np.dtype(dtype).str,
+                                    'data': (block.ptr + offset, False), 'version': 3}
+
+    def __del__(self):
+        b = self._block
+        b.leases -= 1
+        if b.leases == 0:
+            self._arena._give_back(b)
+
+
+class PinnedArena:
+    """Recycles page-locked host blocks (``fluxb200_host_alloc``) across calls:
+    D2H copies into them run at full PCIe rate and asynchronously, and the
+    returned CSR arrays are zero-copy views.  A block is reused only after every
+    array viewing it has been garbage-collected."""
+
+    def __init__(self, max_free_bytes=64 << 30):
+        self.free = []
+        self.max_free_bytes = max_free_bytes
+
+    def take(self, nbytes):
+        nbytes = int(max(nbytes, 1))
+        best = None
+        for b in self.free:
+            if b.nbytes >= nbytes and (best is None or b.nbytes < best.nbytes):
+                best = b
+        if best is not None and best.nbytes <= 2*nbytes + (1 << 20):
+            self.free.remove(best)
+            return best
+        p = ctypes.c_void_p()
+        want = nbytes + nbytes//16 + 4096
+        check(lib().fluxb200_host_alloc(want, ctypes.byref(p)))
+        return _Block(p.value, want)
+
+    def _give_back(self, block):
+        try:
+            self.free.append(block)
+            while sum(b.nbytes for b in self.free) > self.max_free_bytes and self.free:
+                big = max(self.free, key=lambda b: b.nbytes)
+                self.free.remove(big)
+                lib().fluxb200_host_free(big.ptr)
+        except Exception:      # interpreter shutdown
+            pass
+
+    def discard(self, block):
+        """Return a block that was never leased."""
+        self._give_back(block)
+
+    def arrays(self, block, specs):
+        """specs: [(offset_bytes, count, dtype)] -> NumPy arrays viewing the block."""
+        return [np.asarray(_Lease(self, block, off, cnt, dt)) for off, cnt, dt in specs]
+
+
+arena = PinnedArena()

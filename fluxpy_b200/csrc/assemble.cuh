@@ -173,7 +173,8 @@ template <class T> struct FillArgs {
     const int *rank_of_pos; // n: sorted position of original column q
     int m, n, nwords;
     const uint32_t *bits;
-    const int64_t *indptr;  // m + 1 (device, int64)
+    const int64_t *indptr;  // m + 1 (device, int64), local to this launch's rows
+    int64_t out_base;       // position of row 0's first entry in data / indices
     T *data;
     void *indices;          // int32 or int64
     int index_width;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A)
     __shared__ uint32_t running_s;
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row_begin = A.indptr[r];
-    if (A.indptr[r + 1] == row_begin) return;
+    const int64_t row_begin = A.out_base + A.indptr[r];
+    if (A.indptr[r + 1] == A.indptr[r]) return;
     const uint32_t *gbits = A.bits + (size_t)r * A.nwords;
     if (A.bits_in_smem) {
         for (int k = threadIdx.x; k < A.nwords; k += kFillThreads) bits_s[k] = gbits[k];

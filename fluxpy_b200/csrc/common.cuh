@@ -52,6 +52,27 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// grow-only pinned host buffer (small staging: per-sub-slab counts / totals)
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) FB_CUDA(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        FB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

@@ -2,15 +2,15 @@
 // C ABI declared in include/fluxb200.h.  All device work of one handle is
 // enqueued on the handle's own stream.
 #include "../../include/fluxb200.h"
+#include <algorithm>
+#include <string.h>
+#include <vector>
 #include "assemble.cuh"
 #include "common.cuh"
 #include "lbvh.cuh"
 #include "prims.cuh"
 #include "trace.cuh"
 
-#include <algorithm>
-#include <string.h>
-#include <vector>
 
 namespace fluxb200 {
 thread_local std::string g_last_error;
@@ -39,6 +39,14 @@ struct fluxb200_mesh {
     // per-call state
     DevBuf rows, cols, ckeys, cvals, colP, colN, col_face, col_leaf, rank_of_pos, bits, row_counts,
         counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout;
+    // streaming assembly (double-buffered sub-slabs, second stream for fill + D2H)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t slot_free[2] = {};
+    std::vector<cudaEvent_t> sub_events;
+    DevBuf sbits[2], scounts[2], scounts64[2], sindptr[2], stage_data[2], stage_idx[2];
+    HostBuf h_nnz, h_counts;
+    int64_t dev_capacity_hint = 0;
+    int sub_rows_opt = 512;
     size_t m = 0, n = 0;
     int nwords = 0;
     double eps = 0;
@@ -222,8 +230,11 @@ void upload_index_sets(fluxb200_mesh *M, const int64_t *I, size_t m, const int64
     FB_CUDA(cudaStreamSynchronize(M->stream)); // the host vectors go out of scope
 }
 
-template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
-                                 double eps, int64_t *row_counts) {
+// ---- per-call pieces shared by the two-phase and the streaming assembly ---------
+
+// index sets -> device; columns sorted by leaf (Morton) position and gathered
+template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                    double eps) {
     cudaStream_t st = M->stream;
     M->have_count = false;
     M->stats = fluxb200_ff_stats{};
@@ -232,21 +243,11 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
     M->n = n;
     M->eps = eps;
     M->nwords = (int)ceil_div((int64_t)n, 32);
-    const int launches0 = M->sorter.launches;
     int launches = 0;
-
-    FB_CUDA(cudaEventRecord(M->ev[0], st));
     upload_index_sets(M, I, m, J, n);
-    M->row_counts.reserve(sizeof(uint32_t) * std::max<size_t>(m, 1));
-    M->counts64.reserve(sizeof(int64_t) * std::max<size_t>(m, 1));
-    M->indptr.reserve(sizeof(int64_t) * (m + 1));
     M->tested.reserve(sizeof(unsigned long long) * 2);
-    FB_CUDA(cudaMemsetAsync(M->row_counts.p, 0, sizeof(uint32_t) * std::max<size_t>(m, 1), st));
     FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 2, st));
-    FB_CUDA(cudaMemsetAsync(M->indptr.p, 0, sizeof(int64_t) * (m + 1), st));
-
     if (m && n) {
-        // columns in leaf (Morton) order
         M->ckeys.reserve(sizeof(uint64_t) * n);
         M->cvals.reserve(sizeof(uint32_t) * n);
         M->colP.reserve(sizeof(Real4<T>) * n);
@@ -255,6 +256,7 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
         M->col_leaf.reserve(sizeof(int) * n);
         M->rank_of_pos.reserve(sizeof(int) * n);
         const int B = 256;
+        const int l0 = M->sorter.launches;
         col_keys_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(M->cols.as<int>(), (int)n,
                                                                  M->face_leaf.as<int>(),
                                                                  M->ckeys.as<uint64_t>(),
@@ -268,50 +270,96 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
             M->colN.as<Real4<T>>(), M->col_face.as<int>(), M->col_leaf.as<int>(),
             M->rank_of_pos.as<int>());
         FB_CUDA(cudaGetLastError());
-        launches += 2;
-        M->bits.reserve(sizeof(uint32_t) * m * (size_t)M->nwords);
+        launches += 2 + (M->sorter.launches - l0);
     }
-    FB_CUDA(cudaEventRecord(M->ev[1], st));
+    return launches;
+}
 
+// K4 for rows [row0, row0 + mr) of the uploaded index set
+template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, uint32_t *bits,
+                                     uint32_t *row_counts, cudaStream_t st) {
+    TraceArgs<T> A;
+    A.faceP = M->faceP.as<Real4<T>>();
+    A.faceN = M->faceN.as<Real4<T>>();
+    A.rows = M->rows.as<int>() + row0;
+    A.colP = M->colP.as<Real4<T>>();
+    A.colN = M->colN.as<Real4<T>>();
+    A.col_face = M->col_face.as<int>();
+    A.col_leaf = M->col_leaf.as<int>();
+    A.m = (int)mr;
+    A.n = (int)M->n;
+    A.nwords = M->nwords;
+    A.eps = (T)M->eps;
+    A.nodes = M->nodes.as<float4>();
+    A.tri = M->tri.as<float4>();
+    A.nnodes = M->nnodes;
+    A.ntop = M->ntop;
+    A.bits = bits;
+    A.row_counts = row_counts;
+    A.tested = M->tested.as<unsigned long long>();
+    const int nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
+    const int max_seg = (int)ceil_div(nchunks, kTraceWarps);
+    const int64_t target_ctas = (int64_t)M->num_sms * 16;
+    int nseg = (int)std::min<int64_t>(max_seg, std::max<int64_t>(1, ceil_div(target_ctas, (int64_t)mr)));
+    A.chunks_per_seg = (int)ceil_div(nchunks, nseg);
+    A.nseg = (int)ceil_div(nchunks, A.chunks_per_seg);
+    const int64_t grid = (int64_t)mr * A.nseg;
+    FB_REQUIRE(grid < (1ll << 31), "too many row segments for one launch");
+    const size_t smem = sizeof(float4) * 2 * (size_t)M->ntop;
+    FB_REQUIRE((int)smem + 2048 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
+    FB_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)std::max<size_t>(smem, 1024)));
+    trace_kernel<T><<<(unsigned)grid, kTraceThreads, smem, st>>>(A);
+    FB_CUDA(cudaGetLastError());
+}
+
+// K6 for rows [row0, row0 + mr): local indptr (mr + 1) -> data / indices at out_base
+template <class T> void launch_fill(fluxb200_mesh *M, size_t row0, size_t mr, const uint32_t *bits,
+                                    const int64_t *indptr_local, int64_t out_base, T *data, void *indices,
+                                    int index_width, cudaStream_t st) {
+    FillArgs<T> A;
+    A.faceP = M->faceP.as<Real4<T>>();
+    A.faceN = M->faceN.as<Real4<T>>();
+    A.rows = M->rows.as<int>() + row0;
+    A.cols = M->cols.as<int>();
+    A.rank_of_pos = M->rank_of_pos.as<int>();
+    A.m = (int)mr;
+    A.n = (int)M->n;
+    A.nwords = M->nwords;
+    A.bits = bits;
+    A.indptr = indptr_local;
+    A.out_base = out_base;
+    A.data = data;
+    A.indices = indices;
+    A.index_width = index_width;
+    size_t smem = sizeof(uint32_t) * (size_t)M->nwords;
+    A.bits_in_smem = (int)smem + 1024 <= M->max_smem_optin;
+    if (!A.bits_in_smem) smem = 0;
+    FB_CUDA(cudaFuncSetAttribute(fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)std::max<size_t>(smem, 1024)));
+    fill_kernel<T><<<(unsigned)mr, kFillThreads, smem, st>>>(A);
+    FB_CUDA(cudaGetLastError());
+}
+
+// ---- two-phase API: count (all rows, bits kept on the device), then fill ---------
+template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                 double eps, int64_t *row_counts) {
+    cudaStream_t st = M->stream;
+    FB_CUDA(cudaEventRecord(M->ev[0], st));
+    int launches = prepare_call<T>(M, I, m, J, n, eps);
+    M->row_counts.reserve(sizeof(uint32_t) * std::max<size_t>(m, 1));
+    M->counts64.reserve(sizeof(int64_t) * std::max<size_t>(m, 1));
+    M->indptr.reserve(sizeof(int64_t) * (m + 1));
+    FB_CUDA(cudaMemsetAsync(M->row_counts.p, 0, sizeof(uint32_t) * std::max<size_t>(m, 1), st));
+    FB_CUDA(cudaMemsetAsync(M->indptr.p, 0, sizeof(int64_t) * (m + 1), st));
+    if (m && n) M->bits.reserve(sizeof(uint32_t) * m * (size_t)M->nwords);
+    FB_CUDA(cudaEventRecord(M->ev[1], st));
     if (m && n) {
-        TraceArgs<T> A;
-        A.faceP = M->faceP.as<Real4<T>>();
-        A.faceN = M->faceN.as<Real4<T>>();
-        A.rows = M->rows.as<int>();
-        A.colP = M->colP.as<Real4<T>>();
-        A.colN = M->colN.as<Real4<T>>();
-        A.col_face = M->col_face.as<int>();
-        A.col_leaf = M->col_leaf.as<int>();
-        A.m = (int)m;
-        A.n = (int)n;
-        A.nwords = M->nwords;
-        A.eps = (T)eps;
-        A.nodes = M->nodes.as<float4>();
-        A.tri = M->tri.as<float4>();
-        A.nnodes = M->nnodes;
-        A.ntop = M->ntop;
-        A.bits = M->bits.as<uint32_t>();
-        A.row_counts = M->row_counts.as<uint32_t>();
-        A.tested = M->tested.as<unsigned long long>();
-        const int nchunks = (int)ceil_div((int64_t)n, kChunkCols);
-        const int max_seg = (int)ceil_div(nchunks, kTraceWarps);
-        const int64_t target_ctas = (int64_t)M->num_sms * 16;
-        int nseg = (int)std::min<int64_t>(max_seg, std::max<int64_t>(1, ceil_div(target_ctas, (int64_t)m)));
-        A.chunks_per_seg = (int)ceil_div(nchunks, nseg);
-        A.nseg = (int)ceil_div(nchunks, A.chunks_per_seg);
-        const int64_t grid = (int64_t)m * A.nseg;
-        FB_REQUIRE(grid < (1ll << 31), "too many row segments for one launch");
-        const size_t smem = sizeof(float4) * 2 * (size_t)M->ntop;
-        FB_REQUIRE((int)smem + 2048 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
-        FB_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)std::max<size_t>(smem, 1024)));
-        trace_kernel<T><<<(unsigned)grid, kTraceThreads, smem, st>>>(A);
-        FB_CUDA(cudaGetLastError());
+        launch_trace<T>(M, 0, m, M->bits.as<uint32_t>(), M->row_counts.as<uint32_t>(), st);
         launches += 1;
         M->stats.trace_launches = 1;
     }
     FB_CUDA(cudaEventRecord(M->ev[2], st));
-
     if (m) {
         counts_to_i64_kernel<<<blocks_for((int64_t)m, 256), 256, 0, st>>>(M->row_counts.as<uint32_t>(),
                                                                          (int)m, M->counts64.as<int64_t>());
@@ -333,7 +381,7 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_prepare, M->ev[0], M->ev[1]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_trace, M->ev[1], M->ev[2]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_scan, M->ev[2], M->ev[3]));
-    M->stats.kernel_launches = launches + (M->sorter.launches - launches0);
+    M->stats.kernel_launches = launches;
     M->have_count = true;
 }
 
@@ -361,27 +409,8 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_CUDA(cudaEventRecord(M->ev[0], st));
     int launches = 0;
     if (m && n && nnz) {
-        FillArgs<T> A;
-        A.faceP = M->faceP.as<Real4<T>>();
-        A.faceN = M->faceN.as<Real4<T>>();
-        A.rows = M->rows.as<int>();
-        A.cols = M->cols.as<int>();
-        A.rank_of_pos = M->rank_of_pos.as<int>();
-        A.m = (int)m;
-        A.n = (int)n;
-        A.nwords = M->nwords;
-        A.bits = M->bits.as<uint32_t>();
-        A.indptr = M->indptr.as<int64_t>();
-        A.data = d_data;
-        A.indices = d_indices;
-        A.index_width = index_width;
-        size_t smem = sizeof(uint32_t) * (size_t)M->nwords;
-        A.bits_in_smem = (int)smem + 1024 <= M->max_smem_optin;
-        if (!A.bits_in_smem) smem = 0;
-        FB_CUDA(cudaFuncSetAttribute(fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)std::max<size_t>(smem, 1024)));
-        fill_kernel<T><<<(unsigned)m, kFillThreads, smem, st>>>(A);
-        FB_CUDA(cudaGetLastError());
+        launch_fill<T>(M, 0, m, M->bits.as<uint32_t>(), M->indptr.as<int64_t>(), 0, d_data, d_indices,
+                       index_width, st);
         ++launches;
     }
     void *d_indptr = M->indptr.p;
@@ -407,6 +436,163 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_fill, M->ev[0], M->ev[1]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_d2h, M->ev[1], M->ev[2]));
     M->stats.kernel_launches += launches;
+}
+
+// ---- streaming assembly: row sub-slabs pipelined over two streams ------------------
+// compute stream: trace(k) -> counts(k) -> local indptr(k) -> nnz(k), counts(k) to pinned host
+// copy stream   : fill(k) -> D2H(k)   (runs under trace(k+1); bits / staging double-buffered)
+// Returns false when `capacity` entries do not suffice (stats.nnz = entries needed).
+template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                                    double eps, int index_width, int destination, void *indptr,
+                                    void *indices, void *data, int64_t capacity, int64_t *row_counts) {
+    FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
+    FB_REQUIRE(destination == 0 || destination == 2, "destination must be 0 (host) or 2 (library device buffers)");
+    if (index_width == 4) FB_REQUIRE(n < (1ull << 31), "int32 indices cannot hold this many columns");
+    cudaStream_t s0 = M->stream, s1 = M->copy_stream;
+    FB_CUDA(cudaEventRecord(M->ev[0], s0));
+    int launches = prepare_call<T>(M, I, m, J, n, eps);
+    FB_CUDA(cudaEventRecord(M->ev[1], s0));
+    const size_t sub = std::max<size_t>(1, std::min<size_t>((size_t)M->sub_rows_opt, std::max<size_t>(m, 1)));
+    const size_t nsub = m ? (size_t)ceil_div((int64_t)m, (int64_t)sub) : 0;
+    // per-slot (double-buffered) device state
+    for (int b = 0; b < 2; ++b) {
+        M->sbits[b].reserve(sizeof(uint32_t) * sub * (size_t)std::max(M->nwords, 1));
+        M->scounts[b].reserve(sizeof(uint32_t) * sub);
+        M->scounts64[b].reserve(sizeof(int64_t) * sub);
+        M->sindptr[b].reserve(sizeof(int64_t) * (sub + 1));
+    }
+    M->h_nnz.reserve(sizeof(int64_t) * std::max<size_t>(nsub, 1));
+    M->h_counts.reserve(sizeof(uint32_t) * std::max<size_t>(m, 1));
+    while (M->sub_events.size() < 3 * nsub) {
+        cudaEvent_t e;
+        FB_CUDA(cudaEventCreate(&e));
+        M->sub_events.push_back(e);
+    }
+    if (destination == 2) {
+        if (capacity <= 0)
+            capacity = M->dev_capacity_hint > 0
+                           ? M->dev_capacity_hint
+                           : std::max<int64_t>(1024, (int64_t)(0.62 * (double)m * (double)n));
+        capacity = std::min<int64_t>(capacity, std::max<int64_t>((int64_t)m * (int64_t)n, 1));
+        M->out_data.reserve(sizeof(T) * (size_t)capacity);
+        M->out_indices.reserve((size_t)index_width * (size_t)capacity);
+    }
+    int64_t *h_nnz = M->h_nnz.as<int64_t>();
+    uint32_t *h_counts = M->h_counts.as<uint32_t>();
+    int64_t total = 0;
+    bool overflow = false;
+    float ms_fill = 0.f;
+
+    auto enqueue_trace = [&](size_t k) {
+        const int b = (int)(k & 1);
+        const size_t row0 = k * sub, mr = std::min(sub, m - row0);
+        if (k >= 2) FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0)); // fill(k-2) done with slot b
+        FB_CUDA(cudaMemsetAsync(M->scounts[b].p, 0, sizeof(uint32_t) * mr, s0));
+        FB_CUDA(cudaEventRecord(M->sub_events[3 * k], s0));
+        if (n) launch_trace<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->scounts[b].as<uint32_t>(), s0);
+        FB_CUDA(cudaEventRecord(M->sub_events[3 * k + 1], s0));
+        counts_to_i64_kernel<<<blocks_for((int64_t)mr, 256), 256, 0, s0>>>(M->scounts[b].as<uint32_t>(), (int)mr,
+                                                                          M->scounts64[b].as<int64_t>());
+        scan_exclusive<int64_t, int64_t>(M->scounts64[b].as<int64_t>(), M->sindptr[b].as<int64_t>(), (int64_t)mr,
+                                         M->sindptr[b].as<int64_t>() + mr, s0);
+        FB_CUDA(cudaMemcpyAsync(h_nnz + k, M->sindptr[b].as<int64_t>() + mr, sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, s0));
+        FB_CUDA(cudaMemcpyAsync(h_counts + row0, M->scounts[b].p, sizeof(uint32_t) * mr, cudaMemcpyDeviceToHost, s0));
+        FB_CUDA(cudaEventRecord(M->sub_events[3 * k + 2], s0));
+        launches += (n ? 1 : 0) + 2;
+    };
+    auto finish = [&](size_t k) {
+        const int b = (int)(k & 1);
+        const size_t row0 = k * sub, mr = std::min(sub, m - row0);
+        FB_CUDA(cudaEventSynchronize(M->sub_events[3 * k + 2]));
+        const int64_t nnz_k = h_nnz[k], off = total;
+        total += nnz_k;
+        if (index_width == 4 && total >= (1ll << 31)) throw CudaError{"int32 indices cannot hold this matrix"};
+        if (total > capacity) overflow = true;
+        FB_CUDA(cudaStreamWaitEvent(s1, M->sub_events[3 * k + 2], 0));
+        if (!overflow && nnz_k) {
+            T *d_data;
+            void *d_idx;
+            int64_t base;
+            if (destination == 2) {
+                d_data = M->out_data.as<T>();
+                d_idx = M->out_indices.p;
+                base = off;
+            } else {
+                M->stage_data[b].reserve(sizeof(T) * (size_t)nnz_k);
+                M->stage_idx[b].reserve((size_t)index_width * (size_t)nnz_k);
+                d_data = M->stage_data[b].as<T>();
+                d_idx = M->stage_idx[b].p;
+                base = 0;
+            }
+            launch_fill<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->sindptr[b].as<int64_t>(), base, d_data,
+                           d_idx, index_width, s1);
+            ++launches;
+            if (destination == 0) {
+                FB_CUDA(cudaMemcpyAsync((char *)data + sizeof(T) * (size_t)off, d_data, sizeof(T) * (size_t)nnz_k,
+                                        cudaMemcpyDeviceToHost, s1));
+                FB_CUDA(cudaMemcpyAsync((char *)indices + (size_t)index_width * (size_t)off, d_idx,
+                                        (size_t)index_width * (size_t)nnz_k, cudaMemcpyDeviceToHost, s1));
+            }
+        }
+        FB_CUDA(cudaEventRecord(M->slot_free[b], s1));
+    };
+
+    FB_CUDA(cudaEventRecord(M->ev[4], s1));
+    for (size_t k = 0; k < nsub; ++k) {
+        enqueue_trace(k);
+        if (k >= 1) finish(k - 1);
+    }
+    if (nsub) finish(nsub - 1);
+    FB_CUDA(cudaEventRecord(M->ev[5], s1));
+    FB_CUDA(cudaEventRecord(M->ev[2], s0));
+    unsigned long long tested = 0;
+    FB_CUDA(cudaMemcpyAsync(&tested, M->tested.p, sizeof(tested), cudaMemcpyDeviceToHost, s0));
+    FB_CUDA(cudaStreamSynchronize(s0));
+    FB_CUDA(cudaStreamSynchronize(s1));
+    // leave the handle's main stream ordered after the copy stream
+    M->nnz = total;
+    M->stats.nnz = total;
+    M->stats.pairs_tested = (int64_t)tested;
+    M->dev_capacity_hint = std::max<int64_t>(M->dev_capacity_hint, total + total / 16);
+    float ms = 0.f;
+    M->stats.ms_trace = 0.f;
+    for (size_t k = 0; k < nsub; ++k) {
+        FB_CUDA(cudaEventElapsedTime(&ms, M->sub_events[3 * k], M->sub_events[3 * k + 1]));
+        M->stats.ms_trace += ms;
+        FB_CUDA(cudaEventElapsedTime(&ms, M->sub_events[3 * k + 1], M->sub_events[3 * k + 2]));
+        M->stats.ms_scan += ms;
+    }
+    FB_CUDA(cudaEventElapsedTime(&M->stats.ms_prepare, M->ev[0], M->ev[1]));
+    FB_CUDA(cudaEventElapsedTime(&ms_fill, M->ev[4], M->ev[5]));
+    M->stats.ms_fill = ms_fill; // span of the copy stream: fills + D2H, overlapped with tracing
+    M->stats.ms_d2h = 0.f;
+    M->stats.trace_launches = (int)nsub;
+    M->stats.kernel_launches = launches;
+    if (row_counts)
+        for (size_t r = 0; r < m; ++r) row_counts[r] = (int64_t)h_counts[r];
+    if (overflow) return false;
+    if (destination == 0 && indptr) { // global indptr on the host, in the index dtype
+        int64_t run = 0;
+        if (index_width == 4) {
+            int32_t *ip = reinterpret_cast<int32_t *>(indptr);
+            ip[0] = 0;
+            for (size_t r = 0; r < m; ++r) ip[r + 1] = (int32_t)(run += h_counts[r]);
+        } else {
+            int64_t *ip = reinterpret_cast<int64_t *>(indptr);
+            ip[0] = 0;
+            for (size_t r = 0; r < m; ++r) ip[r + 1] = (run += h_counts[r]);
+        }
+    }
+    if (destination == 2) { // device indptr for downstream device consumers
+        M->indptr.reserve(sizeof(int64_t) * (m + 1));
+        std::vector<int64_t> ip(m + 1, 0);
+        for (size_t r = 0; r < m; ++r) ip[r + 1] = ip[r] + h_counts[r];
+        FB_CUDA(cudaMemcpyAsync(M->indptr.p, ip.data(), sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, s0));
+        FB_CUDA(cudaStreamSynchronize(s0));
+        M->have_count = true; // fluxb200_ff_device_csr is valid
+    }
+    return true;
 }
 
 template <class T> void visibility(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
@@ -488,6 +674,8 @@ int fluxb200_mesh_create(const void *V, size_t nv, const int64_t *F, size_t nf, 
         M->nv = nv;
         M->nf = nf;
         FB_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
+        FB_CUDA(cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : M->slot_free) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : M->ev) FB_CUDA(cudaEventCreate(&e));
         FB_CUDA(cudaDeviceGetAttribute(&M->num_sms, cudaDevAttrMultiProcessorCount, device));
         FB_CUDA(cudaDeviceGetAttribute(&M->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -527,6 +715,14 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
                           &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};
         for (DevBuf *b : bufs) b->release();
+        for (int k = 0; k < 2; ++k) {
+            M->sbits[k].release(); M->scounts[k].release(); M->scounts64[k].release(); M->sindptr[k].release();
+            M->stage_data[k].release(); M->stage_idx[k].release();
+            if (M->slot_free[k]) cudaEventDestroy(M->slot_free[k]);
+        }
+        M->h_nnz.release(); M->h_counts.release();
+        for (auto &e : M->sub_events) cudaEventDestroy(e);
+        if (M->copy_stream) { cudaStreamSynchronize(M->copy_stream); cudaStreamDestroy(M->copy_stream); }
         M->sorter.release();
         for (auto &e : M->ev)
             if (e) cudaEventDestroy(e);
@@ -607,6 +803,42 @@ int fluxb200_ff_fill(fluxb200_mesh *M, int index_width, int destination, void *i
         DeviceGuard guard(M->device);
         DISPATCH(M, ff_fill, M, index_width, destination, indptr, indices, data);
         if (stats) *stats = M->stats;
+    });
+}
+
+int fluxb200_ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n, double eps,
+                         int index_width, int destination, void *indptr, void *indices, void *data,
+                         int64_t capacity, int64_t *row_counts, fluxb200_ff_stats *stats) {
+    bool ok = true;
+    int rc = guarded([&] {
+        FB_REQUIRE(M, "mesh is NULL");
+        DeviceGuard guard(M->device);
+        if (M->dtype == FLUXB200_F64)
+            ok = ff_assemble<double>(M, I, m, J, n, eps, index_width, destination, indptr, indices, data,
+                                     capacity, row_counts);
+        else
+            ok = ff_assemble<float>(M, I, m, J, n, eps, index_width, destination, indptr, indices, data,
+                                    capacity, row_counts);
+        if (stats) *stats = M->stats;
+    });
+    if (rc) return rc;
+    if (!ok) {
+        set_error("capacity too small for the assembled matrix (stats.nnz entries needed)");
+        return FLUXB200_OVERFLOW;
+    }
+    return 0;
+}
+
+int fluxb200_host_alloc(size_t bytes, void **ptr) {
+    return guarded([&] {
+        FB_REQUIRE(ptr, "ptr is NULL");
+        FB_CUDA(cudaHostAlloc(ptr, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+    });
+}
+
+int fluxb200_host_free(void *ptr) {
+    return guarded([&] {
+        if (ptr) FB_CUDA(cudaFreeHost(ptr));
     });
 }
 
@@ -720,6 +952,9 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->top_nodes_opt = (int)value;
             M->have_count = false;
             bvh_build(M);
+        } else if (s == "sub_rows") {
+            FB_REQUIRE(value >= 1 && value <= (1 << 20), "sub_rows out of range");
+            M->sub_rows_opt = (int)value;
         } else if (s == "trace_mode") {
             FB_REQUIRE(value == 0, "unknown trace_mode");
             M->trace_mode = (int)value;

@@ -1,8 +1,9 @@
 """Mirror of ``flux.form_factors.get_form_factor_matrix``
 (reference src/flux/form_factors.py:11-72) on the fused CUDA path.
 
-One FFI round trip per matrix (count, then fill) instead of one ray-tracing
-call per row; the result is the same ``scipy.sparse.csr_matrix``: shape
+One FFI call per matrix (``fluxb200_ff_assemble``: row sub-slabs traced, filled
+and copied out in a two-stream pipeline into page-locked host buffers) instead
+of one ray-tracing call per row; the result is the same ``scipy.sparse.csr_matrix``: shape
 ``(len(I), len(J))``, ``data`` in ``shape_model.dtype``, column indices =
 positions into ``J`` ascending within each row, index arrays int32 when they
 fit (what SciPy makes of the reference's uint64 arrays) and int64 otherwise.
@@ -21,13 +22,10 @@ def get_form_factor_matrix(shape_model, I=None, J=None, eps=None):
         eps = config.DEFAULT_EPS
     if shape_model.dtype not in (np.float32, np.float64):
         raise RuntimeError(f'unsupported dtype {shape_model.dtype}')   # form_factors.py:37
-    if not hasattr(shape_model, '_ff_count'):
+    if not hasattr(shape_model, '_ff_assemble_host'):
         raise RuntimeError('get_form_factor_matrix needs a CudaTrimeshShapeModel: '
                            'this package has no CPU path')
-    m, n, _, st = shape_model._ff_count(I, J, eps, want_row_counts=False)
-    nnz = int(st.nnz)
-    index_dtype = np.int32 if max(nnz, n, m + 1) < 2**31 else np.int64
-    indptr, indices, data, st = shape_model._ff_fill_host(m, nnz, index_dtype)
+    m, n, indptr, indices, data, _, st = shape_model._ff_assemble_host(I, J, eps)
     last_stats.clear()
     last_stats.update(st.as_dict())
     FF = scipy.sparse.csr_matrix((data, indices, indptr), shape=(m, n), copy=False)

@@ -262,6 +262,74 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
+    #: running estimate of nnz / (m*n), used to size the streaming output buffers
+    _fill_ratio = 0.6
+
+    def _ff_assemble_host(self, I, J, eps, want_row_counts=False):
+        """Streaming assembly (``fluxb200_ff_assemble``) into page-locked host
+        buffers from the arena; returns zero-copy NumPy views trimmed to nnz.
+        Falls back to one retry with the exact size when the estimate was short."""
+        self._sync_face_data()
+        I = None if I is None else _index_array(I)
+        J = None if J is None else _index_array(J)
+        m = self._nf if I is None else len(I)
+        n = self._nf if J is None else len(J)
+        L = _lib.lib()
+        counts = np.empty(m, np.int64) if want_row_counts else None
+        st = _lib.FFStats()
+        esz = np.dtype(self.dtype).itemsize
+        cap = int(min(m*n, max(1024, self._fill_ratio*1.08*m*n + 4096)))
+        while True:
+            idt = np.int32 if max(cap, n, m + 1) < 2**31 else np.int64
+            isz = np.dtype(idt).itemsize
+            off_idx = -(-(cap*esz)//256)*256
+            off_ptr = off_idx + -(-(cap*isz)//256)*256
+            block = _lib.arena.take(off_ptr + (m + 1)*isz)
+            rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), isz, 0,
+                                        block.ptr + off_ptr, block.ptr + off_idx, block.ptr, cap,
+                                        _lib.ptr(counts), ctypes.byref(st))
+            if rc == _lib.OVERFLOW:
+                _lib.arena.discard(block)
+                cap = int(st.nnz)
+                continue
+            if rc:
+                _lib.arena.discard(block)
+                _lib.check(rc)
+            break
+        nnz = int(st.nnz)
+        if m*n:
+            type(self)._fill_ratio = max(0.02, nnz/(m*n))
+        data, indices, indptr = _lib.arena.arrays(
+            block, [(0, nnz, self.dtype), (off_idx, nnz, idt), (off_ptr, m + 1, idt)])
+        return m, n, indptr, indices, data, counts, st
+
+    def _ff_assemble_device(self, I, J, eps, index_width=4, want_row_counts=False):
+        """Streaming assembly into library-owned device buffers (CSR stays in HBM)."""
+        self._sync_face_data()
+        I = None if I is None else _index_array(I)
+        J = None if J is None else _index_array(J)
+        m = self._nf if I is None else len(I)
+        n = self._nf if J is None else len(J)
+        L = _lib.lib()
+        counts = np.empty(m, np.int64) if want_row_counts else None
+        st = _lib.FFStats()
+        cap = 0
+        for attempt in range(3):
+            rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), index_width,
+                                        2, None, None, None, cap, _lib.ptr(counts), ctypes.byref(st))
+            if rc != _lib.OVERFLOW:
+                break
+            cap = int(st.nnz) + 1
+        _lib.check(rc)
+        return m, n, counts, st
+
+    def device_csr(self):
+        """(indptr, indices, data) device pointers + nnz of the device-resident CSR."""
+        ip, ix, dv, nnz = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(_lib.lib().fluxb200_ff_device_csr(self._handle, ctypes.byref(ip), ctypes.byref(ix),
+                                                     ctypes.byref(dv), ctypes.byref(nnz)))
+        return ip.value, ix.value, dv.value, nnz.value
+
     def bvh_info(self):
         info = _lib.BvhInfo()
         _lib.check(_lib.lib().fluxb200_bvh_info_get(self._handle, ctypes.byref(info)))

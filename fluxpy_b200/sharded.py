@@ -74,18 +74,17 @@ def get_form_factor_matrix_sharded(shape_model, I=None, J=None, eps=None, group=
     I = np.arange(nf, dtype=np.int64) if I is None else np.asarray(I).astype(np.int64)
     starts = slab_bounds(len(I), world, weights)
     lo, hi = int(starts[rank]), int(starts[rank + 1])
-    m, n, counts, st = shape_model._ff_count(I[lo:hi], J, eps, want_row_counts=True)
+    local = None
+    if to_host:
+        m, n, ip, ix, dv, counts, st = shape_model._ff_assemble_host(I[lo:hi], J, eps, want_row_counts=True)
+        local = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n), copy=False)
+        local.has_sorted_indices = True
+    else:
+        m, n, counts, st = shape_model._ff_assemble_device(I[lo:hi], J, eps, 4, want_row_counts=True)
     dev = None
     if dist.get_backend(group) == 'nccl':
         import torch
         dev = torch.device('cuda', shape_model.device)
+    # the one collective of the path: per-row counts -> global indptr on every rank
     indptr = exchange_row_counts(counts, starts, group, dev)
-    local = None
-    if to_host:
-        nnz = int(st.nnz)
-        idt = np.int32 if max(nnz, n, m + 1) < 2**31 else np.int64
-        ip, ix, dv, st = shape_model._ff_fill_host(m, nnz, idt)
-        local = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n), copy=False)
-    else:
-        st = shape_model._ff_fill_device(4 if max(int(st.nnz), n) < 2**31 else 8)
     return SlabResult(lo, hi, indptr, local, st.as_dict())

@@ -34,7 +34,11 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 1
+#define FLUXB200_ABI_VERSION 2
+
+#define FLUXB200_OK 0
+#define FLUXB200_ERROR 1
+#define FLUXB200_OVERFLOW 2 /* fluxb200_ff_assemble: `capacity` too small, see stats.nnz */
 
 typedef struct fluxb200_mesh fluxb200_mesh; /* cf. struct cgal_aabb, aabb_wrapper.h:6 */
 
@@ -113,7 +117,24 @@ int fluxb200_ff_count(fluxb200_mesh *mesh, const int64_t *I, size_t m, const int
  * Columns are positions into J, ascending within each row (form_factors.py:52,69). */
 int fluxb200_ff_fill(fluxb200_mesh *mesh, int index_width, int destination, void *indptr,
                      void *indices, void *data, fluxb200_ff_stats *stats);
-/* Device pointers of the library-owned CSR of the last destination==2 fill. */
+/* One-call streaming form of the two passes above (what get_form_factor_matrix
+ * uses): rows are processed in sub-slabs; while sub-slab k+1 is traced on the
+ * handle's stream, sub-slab k is filled and copied out on a second stream.
+ * destination 0: host buffers holding `capacity` entries (indices, data) and
+ *                m+1 indptr entries; page-locked buffers (fluxb200_host_alloc)
+ *                make the copies asynchronous.  Returns FLUXB200_OVERFLOW with
+ *                stats->nnz = entries needed when capacity is too small
+ *                (nothing usable was written; call again with more room).
+ * destination 2: library-owned device buffers (grown as needed; capacity <= 0
+ *                uses the previous size as the first guess).
+ * row_counts: optional int64[m] (host). */
+int fluxb200_ff_assemble(fluxb200_mesh *mesh, const int64_t *I, size_t m, const int64_t *J, size_t n,
+                         double eps, int index_width, int destination, void *indptr, void *indices,
+                         void *data, int64_t capacity, int64_t *row_counts, fluxb200_ff_stats *stats);
+/* Page-locked host memory for the CSR outputs (cudaHostAlloc / cudaFreeHost). */
+int fluxb200_host_alloc(size_t bytes, void **ptr);
+int fluxb200_host_free(void *ptr);
+/* Device pointers of the library-owned CSR of the last destination==2 fill / assemble. */
 int fluxb200_ff_device_csr(fluxb200_mesh *mesh, void **indptr, void **indices, void **data,
                            int64_t *nnz);
 
@@ -155,7 +176,7 @@ int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *st
  * caller can bracket calls with its own events. */
 int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
 /* Tunables: "top_nodes" (BVH nodes staged in shared memory), "trace_mode"
- * (0 = per-ray stackless, 1 = warp-packet stackless), "rows_per_launch". */
+ * (0 = per-ray stackless), "sub_rows" (rows per sub-slab of fluxb200_ff_assemble). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 
 #ifdef __cplusplus

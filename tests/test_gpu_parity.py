@@ -271,3 +271,42 @@ def test_slab_properties_at_full_size(mods):
     om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
     samp = np.array([0, 77777, 150001, nf - 1])
     assert same_csr(gf(sm, samp), mods['oracle'].get_form_factor_matrix(om, samp))
+
+
+def test_streaming_and_two_phase_paths_agree(mods):
+    """fluxb200_ff_assemble (sub-slab pipeline, pinned arena, overflow retry,
+    device-resident CSR) == fluxb200_ff_count + fluxb200_ff_fill, bit for bit."""
+    import ctypes
+    import scipy.sparse
+    from fluxpy_b200 import _lib
+    V, F = mods['meshes'].gaussian_crater(40, 2, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N)
+    nf = sm.num_faces
+    rng = np.random.default_rng(3)
+    I = rng.permutation(nf)[:1500]
+    J = rng.permutation(nf)[:2000]
+    m, n, counts, st = sm._ff_count(I, J, 1e-5)
+    ip, ix, dv, _ = sm._ff_fill_host(m, int(st.nnz), np.int32)
+    ref = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n))
+    for sub in (7, 64, 512, 4096):
+        sm.set_option('sub_rows', sub)
+        type(sm)._fill_ratio = 0.05            # force the overflow + retry path
+        FF = mods['ff'].get_form_factor_matrix(sm, I, J)
+        assert same_csr(FF, ref)
+        m2, n2, ip2, ix2, dv2, c2, st2 = sm._ff_assemble_host(I, J, 1e-5, want_row_counts=True)
+        assert np.array_equal(c2, counts) and st2.nnz == st.nnz and st2.pairs_tested == st.pairs_tested
+        # int64 index path of the two-phase API
+        ip8, ix8, dv8, _ = (lambda r: r)(sm._ff_count(I, J, 1e-5)) and sm._ff_fill_host(m, int(st.nnz), np.int64)
+        assert np.array_equal(ix8, ix) and ix8.dtype == np.int64 and np.array_equal(dv8, dv)
+        # device-resident CSR
+        m3, n3, c3, st3 = sm._ff_assemble_device(I, J, 1e-5, 4, want_row_counts=True)
+        assert np.array_equal(c3, counts) and st3.nnz == st.nnz
+        dip, dix, ddv, nnz = sm.device_csr()
+        assert nnz == st.nnz and dip and dix and ddv
+    # results keep their values after the arena recycles other blocks
+    keep = mods['ff'].get_form_factor_matrix(sm, I, J)
+    snapshot = keep.data.copy()
+    for _ in range(3):
+        mods['ff'].get_form_factor_matrix(sm, I[:100], J)
+    assert np.array_equal(keep.data, snapshot)

@@ -58,40 +58,51 @@ template <class T> struct TraceArgs {
     const Real4<T> *colP, *colN;    // n columns gathered in leaf (Morton) order
     const int *col_face, *col_leaf; // face id / leaf position of sorted column s
     int m, n, nwords;               // nwords = ceil(n/32)
-    int nseg, chunks_per_seg;       // column segmentation of a row over CTAs
+    int nchunks;                    // ceil(n / kChunkCols)
     T eps;
     const float4 *nodes, *tri;
-    int nnodes, ntop;
+    int ninternal, ntop, nfaces;
     uint32_t *bits;                 // m x nwords visibility words, sorted-column order
     uint32_t *row_counts;           // m
-    unsigned long long *tested;     // 1
+    unsigned long long *tested;     // [0] rays traced, [1] work-unit counter of this launch
+    int *error_flag;
 };
 
-// K4.  One CTA = one row (source face i) x one segment of Morton-ordered
-// columns.  Each warp owns chunks of 1024 columns:
-//   phase 1  geometric cull, 32 coalesced column loads per lane, survivors as
-//            32 ballot words (lane k keeps word k);
+constexpr int kLeafCap = 8; // deferred candidate triangles per lane
+
+// K4, persistent and warp-centric.  A work unit is one (row, chunk of 1024
+// Morton-ordered columns); every warp of the grid pulls units from one global
+// counter, consecutive units being consecutive chunks of the same row (so the
+// warps in flight share the source face and neighbouring targets).  Per unit:
+//   phase 1  geometric cull: 32 coalesced float4 column loads per lane, the
+//            survivors as 32 ballot words (lane k keeps word k);
 //   phase 2  survivors are compacted 32 at a time (prefix of popcounts +
-//            find-nth-set-bit) so every lane of a trace batch holds a ray;
-//            occluded rays clear their bit in the warp's shared words;
+//            find-nth-set-bit) so every lane of a batch holds a ray; the batch
+//            walks the BVH in lockstep (per-lane stack), triangles whose box
+//            and fitted slab are hit go to a per-lane list in shared memory
+//            and are Pluecker-tested in a converged loop; occluded rays clear
+//            their bit in the warp's shared words;
 //   phase 3  the 32 final words go out as one coalesced 128-byte store.
 template <class T>
-__global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs<T> A) {
+__global__ void __launch_bounds__(kTraceThreads, 3) trace_kernel(const TraceArgs<T> A) {
     extern __shared__ float4 smem_top[];
     __shared__ uint32_t words_s[kTraceWarps][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < 2 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
+    __shared__ int leaf_s[kLeafCap][kTraceThreads];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
     __syncthreads();
-    BvhView bvh{A.nodes, smem_top, A.tri, A.ntop, A.nnodes};
+    const BvhView bvh{A.nodes, smem_top, A.tri, A.ntop, A.ninternal, A.nfaces, A.error_flag};
+    const unsigned total_units = (unsigned)A.m * (unsigned)A.nchunks;
+    unsigned long long tested = 0;
 
-    const int r = blockIdx.x / A.nseg, seg = blockIdx.x - r * A.nseg;
-    const int i = A.rows[r];
-    const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
-    const int nchunks = (A.n + kChunkCols - 1) / kChunkCols;
-    const int c_begin = seg * A.chunks_per_seg, c_end = min(nchunks, c_begin + A.chunks_per_seg);
-    unsigned count = 0, tested = 0;
-
-    for (int c = c_begin + warp; c < c_end; c += kTraceWarps) {
+    while (true) {
+        unsigned unit = 0;
+        if (lane == 0) unit = (unsigned)atomicAdd(A.tested + 1, 1ull);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= total_units) break;
+        const int r = (int)(unit / (unsigned)A.nchunks), c = (int)(unit - (unsigned)r * (unsigned)A.nchunks);
+        const int i = A.rows[r];
+        const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
         const int s0 = c * kChunkCols;
         // ---- phase 1: cull -----------------------------------------------------
         uint32_t myword = 0;
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs<T>
             if (lane >= o) incl += y;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        tested += total;
+        tested += (lane == 0) ? total : 0;
         words_s[warp][lane] = myword;
         __syncwarp();
         for (uint32_t base = 0; base < total; base += 32) {
@@ -131,31 +142,79 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs<T>
             }
             const uint32_t wk = __shfl_sync(0xffffffffu, myword, k);
             const uint32_t before = __shfl_sync(0xffffffffu, incl - __popc(myword), k);
+            // ---- ray set-up and the target's own hit distance (converged) ----------
+            Ray ray;
+            int bit = 0, tleaf = -1, tface = 0;
+            float tj = 0.f;
+            bool active = false, blocked = false;
             if (want < total) {
-                const int bit = __fns(wk, 0, (int)(want - before) + 1);
+                bit = __fns(wk, 0, (int)(want - before) + 1);
                 const int s = s0 + k * 32 + bit;
                 const Real4<T> Pj = load_real4<T>(A.colP + s);
-                Ray ray;
-                bool visible = true; // masked pairs: "vis by default" (shape.py:392)
-                if (setup_ray(Pi, Pj, ray))
-                    visible = target_visible(bvh, ray, A.col_leaf[s], A.col_face[s]);
-                if (!visible) atomicAnd(&words_s[warp][k], ~(1u << bit));
+                if (setup_ray(Pi, Pj, ray)) { // else masked pair: "vis by default" (shape.py:392)
+                    tleaf = A.col_leaf[s];
+                    tface = A.col_face[s];
+                    if (target_hit_t(bvh, ray, tleaf, tj)) active = A.ninternal > 0;
+                    else blocked = true; // the ray misses its own target: closest hit is not j
+                }
             }
+            // ---- lockstep traversal with deferred leaf tests ---------------------------
+            const RayBox rb = make_raybox(ray);
+            const float tmax = tj * 1.000002f;
+            int stack[kStackDepth];
+            int sp = 0, node = 0, nl = 0;
+            auto flush = [&]() {
+                int mx = nl;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                for (int q = 0; q < mx; ++q)
+                    if (q < nl && !blocked) blocked = leaf_occludes(bvh, ray, tj, leaf_s[q][tid], tface);
+                nl = 0;
+                if (blocked) active = false;
+            };
+            while (__any_sync(0xffffffffu, active)) {
+                if (active) {
+                    float4 q[6];
+                    load_node(bvh, node, q);
+                    int next = -1;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (child_hit(ray, rb, q[3 * ch], q[3 * ch + 1], q[3 * ch + 2], tmax)) {
+                            const int ref = __float_as_int(q[3 * ch].w);
+                            if (ref < 0) {
+                                if (~ref != tleaf) leaf_s[nl++][tid] = ~ref;
+                            } else if (next < 0) {
+                                next = ref;
+                            } else if (sp < kStackDepth) {
+                                stack[sp++] = ref;
+                            } else {
+                                *A.error_flag = 1;
+                            }
+                        }
+                    }
+                    if (next < 0) {
+                        if (sp == 0) active = false;
+                        else next = stack[--sp];
+                    }
+                    node = next;
+                }
+                if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
+            }
+            flush();
+            if (blocked) atomicAnd(&words_s[warp][k], ~(1u << bit));
         }
         __syncwarp();
         // ---- phase 3: publish -----------------------------------------------------
         const uint32_t fin = words_s[warp][lane];
         const int wi = c * 32 + lane;
         if (wi < A.nwords) A.bits[(size_t)r * A.nwords + wi] = fin;
-        count += __popc(fin);
+        unsigned count = __popc(fin);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if (lane == 0 && count) atomicAdd(&A.row_counts[r], count);
         __syncwarp();
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
-    if (lane == 0) {
-        if (count) atomicAdd(&A.row_counts[r], count);
-        if (tested) atomicAdd(A.tested, (unsigned long long)tested);
-    }
+    if (lane == 0 && tested) atomicAdd(A.tested, tested);
 }
 
 // ---------------------------------------------------------------------------
@@ -241,8 +300,8 @@ __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A)
 template <class T>
 __global__ void visibility_kernel(const Real4<T> *__restrict__ faceP, const int *__restrict__ rows, int m,
                                   const int *__restrict__ cols, int n, const int *__restrict__ face_leaf,
-                                  const float4 *nodes, const float4 *tri, int nnodes, int nf,
-                                  int bruteforce, uint8_t *__restrict__ vis) {
+                                  const float4 *nodes, const float4 *tri, int ninternal, int nf,
+                                  int *error_flag, int bruteforce, uint8_t *__restrict__ vis) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)m * n) return;
     const int p = (int)(idx / n), q = (int)(idx - (int64_t)p * n);
@@ -253,7 +312,7 @@ __global__ void visibility_kernel(const Real4<T> *__restrict__ faceP, const int 
     if (setup_ray(Pi, Pj, ray)) {
         if (bruteforce) visible = target_visible_bruteforce(tri, nf, ray, face_leaf[j], j);
         else {
-            BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+            const BvhView bvh{nodes, nullptr, tri, 0, ninternal, nf, error_flag};
             visible = target_visible(bvh, ray, face_leaf[j], j);
         }
     }
@@ -264,8 +323,8 @@ __global__ void visibility_kernel(const Real4<T> *__restrict__ faceP, const int 
 template <class T>
 __global__ void occluded_kernel(const Real4<T> *__restrict__ faceP, const Real4<T> *__restrict__ faceN,
                                 const int *__restrict__ rows, int m, const T *__restrict__ D, int nd,
-                                int mode, const float4 *nodes, const float4 *tri, int nnodes,
-                                uint8_t *__restrict__ occ) {
+                                int mode, const float4 *nodes, const float4 *tri, int ninternal, int nf,
+                                int *error_flag, uint8_t *__restrict__ occ) {
     const int cols = mode == 2 ? nd : 1;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)m * cols) return;
@@ -281,15 +340,15 @@ __global__ void occluded_kernel(const Real4<T> *__restrict__ faceP, const Real4<
     ray.dx = (float)d[0];
     ray.dy = (float)d[1];
     ray.dz = (float)d[2];
-    BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+    const BvhView bvh{nodes, nullptr, tri, 0, ninternal, nf, error_flag};
     occ[idx] = occluded_anyhit(bvh, ray, __int_as_float(0x7f800000), -1, 0x7fffffff) ? 1 : 0;
 }
 
 __global__ void intersect1_kernel(float ox, float oy, float oz, float dx, float dy, float dz,
-                                  const float4 *nodes, const float4 *tri, int nnodes, int *face_out,
-                                  float *t_out) {
+                                  const float4 *nodes, const float4 *tri, int ninternal, int nf,
+                                  int *error_flag, int *face_out, float *t_out) {
     Ray ray{ox, oy, oz, dx, dy, dz};
-    BvhView bvh{nodes, nullptr, tri, 0, nnodes};
+    const BvhView bvh{nodes, nullptr, tri, 0, ninternal, nf, error_flag};
     float t = __int_as_float(0x7f800000);
     int face;
     closest_hit(bvh, ray, t, face);

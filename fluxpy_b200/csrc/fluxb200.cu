@@ -3,6 +3,7 @@
 // enqueued on the handle's own stream.
 #include "../../include/fluxb200.h"
 #include <algorithm>
+#include <functional>
 #include <string.h>
 #include <vector>
 #include "assemble.cuh"
@@ -28,11 +29,13 @@ struct fluxb200_mesh {
 
     DevBuf V, F, V32, faceP, faceN; // geometry
     // LBVH
-    DevBuf keys, vals, left, right, parent, first, last, box, flags, pre, flag_by_pre, top_before,
+    DevBuf keys, vals, left, right, parent, first, last, box, slab, flags, pre, flag_by_pre, top_before,
         scene, scalars, nodes, tri, face_leaf;
     RadixSorter sorter;
-    int nnodes = 0, ntop = 0, max_depth = 0;
-    int top_nodes_opt = 1024;
+    int nnodes = 0, ninternal = 0, ntop = 0, max_depth = 0;
+    int top_nodes_opt = 256;
+    int slab_limit_opt = 4096;
+    int blocks_per_sm = 3;
     float ms_build = 0.f;
     float scene_h[7] = {};
 
@@ -118,8 +121,11 @@ void bvh_build(fluxb200_mesh *M) {
     const int n = (int)M->nf;
     cudaStream_t st = M->stream;
     M->nnodes = n ? 2 * n - 1 : 0;
+    M->ninternal = n > 1 ? n - 1 : 0;
     M->ntop = 0;
     M->max_depth = 0;
+    M->scalars.reserve(sizeof(int) * 8);
+    FB_CUDA(cudaMemsetAsync(M->scalars.p, 0, sizeof(int) * 8, st));
     if (n == 0) return;
     const int nn = 2 * n - 1;
     M->keys.reserve(sizeof(uint64_t) * n);
@@ -129,21 +135,20 @@ void bvh_build(fluxb200_mesh *M) {
     M->first.reserve(sizeof(int) * n);
     M->last.reserve(sizeof(int) * n);
     M->parent.reserve(sizeof(int) * nn);
-    M->box.reserve(sizeof(float) * 6 * nn);
+    M->box.reserve(sizeof(float) * 9 * nn);
+    M->slab.reserve(sizeof(unsigned) * 2 * nn);
     M->flags.reserve(sizeof(int) * n);
-    M->pre.reserve(sizeof(int) * nn);
-    M->flag_by_pre.reserve(sizeof(int) * nn);
-    M->top_before.reserve(sizeof(int) * nn);
+    M->pre.reserve(sizeof(int) * n);
+    M->flag_by_pre.reserve(sizeof(int) * n);
+    M->top_before.reserve(sizeof(int) * n);
     M->scene.reserve(sizeof(unsigned) * 8);
-    M->scalars.reserve(sizeof(int) * 8);
-    M->nodes.reserve(sizeof(float4) * 2 * nn);
+    M->nodes.reserve(sizeof(float4) * 6 * std::max(n - 1, 1));
     M->tri.reserve(sizeof(float4) * 3 * n);
     M->face_leaf.reserve(sizeof(int) * n);
 
     FB_CUDA(cudaEventRecord(M->ev[0], st));
     const unsigned scene_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
     FB_CUDA(cudaMemcpyAsync(M->scene.p, scene_init, sizeof(scene_init), cudaMemcpyHostToDevice, st));
-    FB_CUDA(cudaMemsetAsync(M->scalars.p, 0, sizeof(int) * 8, st));
     FB_CUDA(cudaMemsetAsync(M->parent.p, 0xff, sizeof(int) * nn, st));
     FB_CUDA(cudaMemsetAsync(M->flags.p, 0, sizeof(int) * n, st));
     const int B = 256, G = blocks_for(n, B);
@@ -160,17 +165,39 @@ void bvh_build(fluxb200_mesh *M) {
                                   M->left.as<int>(), M->right.as<int>(), M->parent.as<int>(),
                                   M->scene.as<unsigned>(), M->box.as<float>(), M->flags.as<int>(),
                                   M->tri.as<float4>(), M->face_leaf.as<int>());
-    const int K = std::max(1, M->top_nodes_opt / 2);
-    const int threshold = n / K; // subtrees with more than n/K leaves: fewer than 2K nodes
+    slab_init_kernel<<<blocks_for(nn, B), B, 0, st>>>(nn, M->box.as<float>(), M->slab.as<unsigned>());
+    slab_extent_kernel<<<G, B, 0, st>>>(n, M->tri.as<float4>(), M->parent.as<int>(), M->first.as<int>(),
+                                        M->last.as<int>(), M->box.as<float>(), M->slab_limit_opt,
+                                        M->slab.as<unsigned>());
     int *scal = M->scalars.as<int>();
-    preorder_kernel<<<blocks_for(nn, B), B, 0, st>>>(n, M->left.as<int>(), M->parent.as<int>(),
-                                                     M->first.as<int>(), M->last.as<int>(), threshold,
-                                                     M->pre.as<int>(), M->flag_by_pre.as<int>(), scal + 1);
-    scan_exclusive<int, int>(M->flag_by_pre.as<int>(), M->top_before.as<int>(), nn, scal + 0, st);
-    flatten_kernel<<<blocks_for(nn, B), B, 0, st>>>(n, M->left.as<int>(), M->right.as<int>(),
-                                                    M->parent.as<int>(), M->pre.as<int>(),
-                                                    M->top_before.as<int>(), M->flag_by_pre.as<int>(),
-                                                    scal + 0, M->box.as<float>(), M->nodes.as<float4>());
+    if (n > 1) {
+        // "top" = the (at most top_nodes) internal nodes with the largest subtrees: an
+        // upward-closed set, so a threshold on the leaf count selects it
+        int threshold = n;
+        if (M->top_nodes_opt > 0 && n - 1 > 0) {
+            std::vector<int> fi(n - 1), la(n - 1);
+            FB_CUDA(cudaMemcpyAsync(fi.data(), M->first.p, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost, st));
+            FB_CUDA(cudaMemcpyAsync(la.data(), M->last.p, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost, st));
+            FB_CUDA(cudaStreamSynchronize(st));
+            for (int k = 0; k < n - 1; ++k) fi[k] = la[k] - fi[k] + 1; // leaf counts
+            const int budget = M->top_nodes_opt;
+            if (n - 1 <= budget) threshold = 0;
+            else {
+                std::nth_element(fi.begin(), fi.begin() + budget, fi.end(), std::greater<int>());
+                threshold = fi[budget]; // counts strictly above the (budget+1)-th largest: <= budget nodes
+            }
+        }
+        preorder_kernel<<<blocks_for(nn, B), B, 0, st>>>(n, M->left.as<int>(), M->parent.as<int>(),
+                                                         M->first.as<int>(), M->last.as<int>(),
+                                                         threshold,
+                                                         M->pre.as<int>(), M->flag_by_pre.as<int>(), scal + 1);
+        scan_exclusive<int, int>(M->flag_by_pre.as<int>(), M->top_before.as<int>(), n - 1, scal + 0, st);
+        flatten_kernel<<<blocks_for(n - 1, B), B, 0, st>>>(n, M->left.as<int>(), M->right.as<int>(),
+                                                           M->pre.as<int>(), M->top_before.as<int>(),
+                                                           M->flag_by_pre.as<int>(), scal + 0,
+                                                           M->box.as<float>(), M->slab.as<unsigned>(),
+                                                           M->scene.as<unsigned>(), M->nodes.as<float4>());
+    }
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaEventRecord(M->ev[1], st));
     int h[2];
@@ -181,12 +208,23 @@ void bvh_build(fluxb200_mesh *M) {
     M->ntop = h[0];
     M->max_depth = h[1];
     FB_REQUIRE(M->ntop <= std::max(M->top_nodes_opt, 1), "internal: top-node budget exceeded");
+    FB_REQUIRE(M->max_depth < kStackDepth - 2,
+               "LBVH deeper than the traversal stack (too many coincident face centroids)");
     for (int k = 0; k < 7; ++k) {
         const unsigned u = sc[k];
         const unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
         memcpy(&M->scene_h[k], &v, 4);
     }
     FB_CUDA(cudaEventElapsedTime(&M->ms_build, M->ev[0], M->ev[1]));
+}
+
+// traversal-stack overflow cannot happen (depth is checked at build time); the
+// device flag is a second line of defence, read after every query
+void check_error_flag(fluxb200_mesh *M) {
+    int flag = 0;
+    FB_CUDA(cudaMemcpyAsync(&flag, M->scalars.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, M->stream));
+    FB_CUDA(cudaStreamSynchronize(M->stream));
+    FB_REQUIRE(flag == 0, "internal: BVH traversal stack overflow");
 }
 
 template <class T> void set_face_data(fluxb200_mesh *M, const void *P, const void *N, const void *A) {
@@ -292,24 +330,24 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.eps = (T)M->eps;
     A.nodes = M->nodes.as<float4>();
     A.tri = M->tri.as<float4>();
-    A.nnodes = M->nnodes;
+    A.ninternal = M->ninternal;
+    A.nfaces = (int)M->nf;
     A.ntop = M->ntop;
     A.bits = bits;
     A.row_counts = row_counts;
     A.tested = M->tested.as<unsigned long long>();
-    const int nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
-    const int max_seg = (int)ceil_div(nchunks, kTraceWarps);
-    const int64_t target_ctas = (int64_t)M->num_sms * 16;
-    int nseg = (int)std::min<int64_t>(max_seg, std::max<int64_t>(1, ceil_div(target_ctas, (int64_t)mr)));
-    A.chunks_per_seg = (int)ceil_div(nchunks, nseg);
-    A.nseg = (int)ceil_div(nchunks, A.chunks_per_seg);
-    const int64_t grid = (int64_t)mr * A.nseg;
-    FB_REQUIRE(grid < (1ll << 31), "too many row segments for one launch");
-    const size_t smem = sizeof(float4) * 2 * (size_t)M->ntop;
-    FB_REQUIRE((int)smem + 2048 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
+    A.error_flag = M->scalars.as<int>() + 6;
+    A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
+    FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
+    const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
+    FB_REQUIRE((int)smem + 16384 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
     FB_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)std::max<size_t>(smem, 1024)));
-    trace_kernel<T><<<(unsigned)grid, kTraceThreads, smem, st>>>(A);
+    FB_CUDA(cudaMemsetAsync(M->tested.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), st));
+    const int64_t units = (int64_t)mr * A.nchunks;
+    const int grid = (int)std::min<int64_t>((int64_t)M->num_sms * M->blocks_per_sm,
+                                            std::max<int64_t>(1, ceil_div(units, kTraceWarps)));
+    trace_kernel<T><<<grid, kTraceThreads, smem, st>>>(A);
     FB_CUDA(cudaGetLastError());
 }
 
@@ -382,6 +420,7 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_trace, M->ev[1], M->ev[2]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_scan, M->ev[2], M->ev[3]));
     M->stats.kernel_launches = launches;
+    check_error_flag(M);
     M->have_count = true;
 }
 
@@ -571,6 +610,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     M->stats.kernel_launches = launches;
     if (row_counts)
         for (size_t r = 0; r < m; ++r) row_counts[r] = (int64_t)h_counts[r];
+    check_error_flag(M);
     if (overflow) return false;
     if (destination == 0 && indptr) { // global indptr on the host, in the index dtype
         int64_t run = 0;
@@ -605,11 +645,13 @@ template <class T> void visibility(fluxb200_mesh *M, const int64_t *I, size_t m,
     FB_REQUIRE(ceil_div(total, 128) < (1ll << 31), "visibility: too many pairs for one call");
     visibility_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>(
         M->faceP.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->cols.as<int>(), (int)n,
-        M->face_leaf.as<int>(), M->nodes.as<float4>(), M->tri.as<float4>(), M->nnodes, (int)M->nf, brute,
+        M->face_leaf.as<int>(), M->nodes.as<float4>(), M->tri.as<float4>(), M->ninternal, (int)M->nf,
+        M->scalars.as<int>() + 6, brute,
         M->qout.as<uint8_t>());
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaMemcpyAsync(vis, M->qout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
+    check_error_flag(M);
 }
 
 template <class T> void is_occluded(fluxb200_mesh *M, const int64_t *I, size_t m, const void *D, size_t nd,
@@ -626,10 +668,12 @@ template <class T> void is_occluded(fluxb200_mesh *M, const int64_t *I, size_t m
     FB_CUDA(cudaMemcpyAsync(M->qtmp.p, D, sizeof(T) * 3 * nd, cudaMemcpyHostToDevice, st));
     occluded_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>(
         M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->qtmp.as<T>(),
-        (int)nd, mode, M->nodes.as<float4>(), M->tri.as<float4>(), M->nnodes, M->qout.as<uint8_t>());
+        (int)nd, mode, M->nodes.as<float4>(), M->tri.as<float4>(), M->ninternal, (int)M->nf,
+        M->scalars.as<int>() + 6, M->qout.as<uint8_t>());
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaMemcpyAsync(occ, M->qout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
+    check_error_flag(M);
 }
 
 } // namespace
@@ -709,7 +753,7 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
         DeviceGuard guard(M->device);
         if (M->stream) cudaStreamSynchronize(M->stream);
         DevBuf *bufs[] = {&M->V, &M->F, &M->V32, &M->faceP, &M->faceN, &M->keys, &M->vals, &M->left, &M->right,
-                          &M->parent, &M->first, &M->last, &M->box, &M->flags, &M->pre, &M->flag_by_pre,
+                          &M->parent, &M->first, &M->last, &M->box, &M->slab, &M->flags, &M->pre, &M->flag_by_pre,
                           &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->rows,
                           &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
@@ -760,7 +804,7 @@ int fluxb200_bvh_info_get(fluxb200_mesh *M, fluxb200_bvh_info *info) {
     return guarded([&] {
         FB_REQUIRE(M && info, "NULL argument");
         info->num_faces = (int64_t)M->nf;
-        info->num_nodes = M->nnodes;
+        info->num_nodes = M->ninternal;
         info->num_top_nodes = M->ntop;
         info->max_depth = M->max_depth;
         info->ms_build = M->ms_build;
@@ -777,7 +821,7 @@ int fluxb200_bvh_export(fluxb200_mesh *M, float *nodes, int32_t *leaf_face) {
         DeviceGuard guard(M->device);
         if (!M->nf) return;
         if (nodes)
-            FB_CUDA(cudaMemcpyAsync(nodes, M->nodes.p, sizeof(float) * 8 * (size_t)M->nnodes,
+            FB_CUDA(cudaMemcpyAsync(nodes, M->nodes.p, sizeof(float) * 24 * (size_t)M->ninternal,
                                     cudaMemcpyDeviceToHost, M->stream));
         if (leaf_face)
             FB_CUDA(cudaMemcpyAsync(leaf_face, M->vals.p, sizeof(int32_t) * M->nf, cudaMemcpyDeviceToHost,
@@ -894,7 +938,8 @@ int fluxb200_intersect1(fluxb200_mesh *M, const double x[3], const double d[3], 
         float *dt = reinterpret_cast<float *>(M->scalars.as<int>() + 5);
         intersect1_kernel<<<1, 1, 0, M->stream>>>((float)x[0], (float)x[1], (float)x[2], (float)d[0],
                                                   (float)d[1], (float)d[2], M->nodes.as<float4>(),
-                                                  M->tri.as<float4>(), M->nnodes, dface, dt);
+                                                  M->tri.as<float4>(), M->ninternal, (int)M->nf,
+                                                  M->scalars.as<int>() + 6, dface, dt);
         FB_CUDA(cudaGetLastError());
         int hface;
         float ht;
@@ -947,8 +992,16 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
         FB_REQUIRE(M && name, "NULL argument");
         DeviceGuard guard(M->device);
         const std::string s(name);
-        if (s == "top_nodes") {
-            FB_REQUIRE(value >= 0 && value * 32 + 4096 <= M->max_smem_optin, "top_nodes out of range");
+        if (s == "slab_limit") {
+            FB_REQUIRE(value >= 0 && value < (1ll << 31), "slab_limit out of range");
+            M->slab_limit_opt = (int)value;
+            M->have_count = false;
+            bvh_build(M);
+        } else if (s == "blocks_per_sm") {
+            FB_REQUIRE(value >= 1 && value <= 8, "blocks_per_sm out of range");
+            M->blocks_per_sm = (int)value;
+        } else if (s == "top_nodes") {
+            FB_REQUIRE(value >= 0 && value * 96 + 16384 <= M->max_smem_optin, "top_nodes out of range");
             M->top_nodes_opt = (int)value;
             M->have_count = false;
             bvh_build(M);

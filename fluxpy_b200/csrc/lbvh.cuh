@@ -1,5 +1,5 @@
 // lbvh.cuh -- K0 face geometry, K1 Morton codes, K3 Karras hierarchy + refit +
-// flattening for stackless ("skip link") traversal.
+// fitted slabs + flattening into 96-byte two-child nodes.
 //
 // Replaces the Embree scene build of EmbreeTrimeshShapeModel._make_scene
 // (reference src/flux/shape.py:296-344) and the NumPy face geometry helpers
@@ -11,16 +11,12 @@
 
 namespace fluxb200 {
 
-// 32-byte BVH node, two float4:
-//   a = (lo.x, lo.y, lo.z, bits(skip))   skip: node to continue with when this
-//                                        subtree is left (-1 = traversal ends)
-//   b = (hi.x, hi.y, hi.z, bits(link))   link >= 0: first child (the second
-//                                        child is reached through the first
-//                                        child's skip); link < 0: leaf holding
-//                                        triangle ~link (index in leaf order)
-// Order: the `ntop` nodes with the largest subtrees first (pre-order among
-// themselves) -- that prefix is what the trace kernel stages in shared memory
-// -- then every other node in pre-order.
+// Node format: see flatten_kernel.  Every child carries, besides its AABB, a
+// SLAB fitted to the surface it bounds: the unit direction of the subtree's
+// area-weighted normal and the extent of its vertices along it.  Centroid-to-
+// centroid rays graze the surface near both ends; the AABB of a sloped patch
+// is mostly empty space above the surface, the fitted slab is as thin as the
+// patch is flat, so most grazing false positives are rejected.
 
 template <class T> struct Real4 { T x, y, z, w; };
 template <> struct __align__(16) Real4<float> { float x, y, z, w; };
@@ -145,8 +141,12 @@ __global__ void morton_kernel(const float *__restrict__ V32, const int *__restri
     for (int k = 0; k < 3; ++k) {
         const float l = fminf(fminf(v0[k], v1[k]), v2[k]), h = fmaxf(fmaxf(v0[k], v1[k]), v2[k]);
         const double c = 0.5f * (l + h);
-        const double slo = ord_flt(scene[k]), shi = ord_flt(scene[3 + k]);
-        const double ext = shi - slo;
+        // one scale for all axes (cubical Morton cells): a flat terrain does not
+        // waste a third of the bits on its thin axis
+        const double slo = ord_flt(scene[k]);
+        const double ext = fmax(fmax((double)ord_flt(scene[3]) - ord_flt(scene[0]),
+                                     (double)ord_flt(scene[4]) - ord_flt(scene[1])),
+                                (double)ord_flt(scene[5]) - ord_flt(scene[2]));
         double u = ext > 0 ? (c - slo) / ext : 0.0;
         u = fmin(fmax(u, 0.0), 1.0);
         const uint64_t q = (uint64_t)fmin(u * 2097152.0, 2097151.0);
@@ -197,11 +197,12 @@ __global__ void karras_kernel(const uint64_t *__restrict__ keys, int n, int *__r
     if (i == 0) parent[0] = -1;
 }
 
-// leaf boxes (padded) + triangles in leaf order + bottom-up refit
+// leaf boxes (padded) + triangles in leaf order + bottom-up refit of boxes and
+// of the area-weighted normal sums (the direction of each node's fitted slab)
 __global__ void refit_kernel(const float *__restrict__ V32, const int *__restrict__ F, int n,
                              const uint32_t *__restrict__ leaf_face, const int *__restrict__ left,
                              const int *__restrict__ right, const int *__restrict__ parent,
-                             const unsigned *__restrict__ scene, float *__restrict__ box /*6 per node*/,
+                             const unsigned *__restrict__ scene, float *__restrict__ box /*9 per node*/,
                              int *__restrict__ flags, float4 *__restrict__ tri,
                              int *__restrict__ face_leaf) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,34 +217,84 @@ __global__ void refit_kernel(const float *__restrict__ V32, const int *__restric
     // padding: the Pluecker test accepts rays that pass a few ulps (of the
     // largest coordinate) outside a triangle; boxes must not be tighter
     const float pad = 1.0e-6f * ord_flt(scene[6]) + 1e-30f;
-    float b[6];
+    float b[9];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         b[c] = fminf(fminf(v0[c], v1[c]), v2[c]) - pad;
         b[3 + c] = fmaxf(fmaxf(v0[c], v1[c]), v2[c]) + pad;
     }
+    const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+    const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+    b[6] = e1y * e2z - e1z * e2y; // area normal (2 * area * unit normal)
+    b[7] = e1z * e2x - e1x * e2z;
+    b[8] = e1x * e2y - e1y * e2x;
     int node = (n - 1) + k;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) box[6 * (size_t)node + c] = b[c];
+    for (int c = 0; c < 9; ++c) box[9 * (size_t)node + c] = b[c];
     if (n == 1) return;
     int p = parent[node];
     while (p >= 0) {
         __threadfence();
         if (atomicAdd(&flags[p], 1) == 0) return; // first child to arrive stops
         const int lc = left[p], rc = right[p];
-        volatile const float *bl = box + 6 * (size_t)lc, *br = box + 6 * (size_t)rc;
+        volatile const float *bl = box + 9 * (size_t)lc, *br = box + 9 * (size_t)rc;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             b[c] = fminf(bl[c], br[c]);
             b[3 + c] = fmaxf(bl[3 + c], br[3 + c]);
+            b[6 + c] = bl[6 + c] + br[6 + c];
         }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) box[6 * (size_t)p + c] = b[c];
+        for (int c = 0; c < 9; ++c) box[9 * (size_t)p + c] = b[c];
         p = parent[p];
     }
 }
 
-// pre-order index, depth and "top" flag of every node, by walking to the root
+// unit slab direction of every node from its area-normal sum (faces of either
+// orientation count the same way only up to sign -- a folded subtree may cancel
+// to ~0, then any fixed direction is as good as another) + slab extent init
+__global__ void slab_init_kernel(int nn, float *__restrict__ box, unsigned *__restrict__ slab /*2 per node*/) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nn) return;
+    float *b = box + 9 * (size_t)x;
+    const float ax = b[6], ay = b[7], az = b[8];
+    const float l = sqrtf(ax * ax + ay * ay + az * az);
+    if (l > 1e-30f && isfinite(l)) {
+        b[6] = ax / l;
+        b[7] = ay / l;
+        b[8] = az / l;
+    } else {
+        b[6] = 0.f;
+        b[7] = 0.f;
+        b[8] = 1.f;
+    }
+    slab[2 * (size_t)x] = 0xffffffffu; // ordered-uint min
+    slab[2 * (size_t)x + 1] = 0u;      // ordered-uint max
+}
+
+// every leaf projects its three vertices on the slab direction of itself and of
+// each ancestor holding at most `limit` leaves (larger nodes keep an open slab)
+__global__ void slab_extent_kernel(int n, const float4 *__restrict__ tri, const int *__restrict__ parent,
+                                   const int *__restrict__ first, const int *__restrict__ last,
+                                   const float *__restrict__ box, int limit, unsigned *__restrict__ slab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 p0 = tri[3 * (size_t)k], p1 = tri[3 * (size_t)k + 1], p2 = tri[3 * (size_t)k + 2];
+    int x = (n - 1) + k;
+    while (x >= 0) {
+        if (x < n - 1 && last[x] - first[x] + 1 > limit) break; // ancestors only get larger
+        const float *b = box + 9 * (size_t)x;
+        const float nx = b[6], ny = b[7], nz = b[8];
+        const float d0 = nx * p0.x + ny * p0.y + nz * p0.z;
+        const float d1 = nx * p1.x + ny * p1.y + nz * p1.z;
+        const float d2 = nx * p2.x + ny * p2.y + nz * p2.z;
+        atomicMin(&slab[2 * (size_t)x], flt_ord(fminf(fminf(d0, d1), d2)));
+        atomicMax(&slab[2 * (size_t)x + 1], flt_ord(fmaxf(fmaxf(d0, d1), d2)));
+        x = parent[x];
+    }
+}
+
+// pre-order index among INTERNAL nodes and "top" flag, by walking to the root
 __global__ void preorder_kernel(int n, const int *__restrict__ left, const int *__restrict__ parent,
                                 const int *__restrict__ first, const int *__restrict__ last,
                                 int top_leaf_threshold, int *__restrict__ pre,
@@ -257,48 +308,52 @@ __global__ void preorder_kernel(int n, const int *__restrict__ left, const int *
         if (p < 0) break;
         const int lc = left[p];
         if (lc == c) idx += 1;
-        else {
-            const int lsize = (lc >= n - 1) ? 1 : 2 * (last[lc] - first[lc] + 1) - 1;
-            idx += 1 + lsize;
-        }
+        else idx += 1 + ((lc >= n - 1) ? 0 : last[lc] - first[lc]); // internals of the left sibling
         c = p;
         ++depth;
     }
-    pre[x] = idx;
-    const int cnt = (x >= n - 1) ? 1 : last[x] - first[x] + 1;
-    flag_by_pre[idx] = cnt > top_leaf_threshold ? 1 : 0;
     atomicMax(max_depth, depth);
+    if (x >= n - 1) return; // leaves are not stored as nodes
+    pre[x] = idx;
+    flag_by_pre[idx] = (last[x] - first[x] + 1) > top_leaf_threshold ? 1 : 0;
 }
 
+// 96-byte internal node = two children, each three float4:
+//   (lo.xyz, bits(ref))  (hi.xyz, slab_min)  (slab_dir.xyz, slab_max)
+// ref >= 0: internal node index, ref < 0: triangle ~ref (leaf order).
+// Order: the ntop internal nodes with the largest subtrees first (pre-order
+// among themselves; the prefix staged in shared memory), then the rest in
+// pre-order.
 __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *__restrict__ right,
-                               const int *__restrict__ parent, const int *__restrict__ pre,
-                               const int *__restrict__ top_before, const int *__restrict__ flag_by_pre,
-                               const int *__restrict__ ntop_p, const float *__restrict__ box,
-                               float4 *__restrict__ nodes) {
+                               const int *__restrict__ pre, const int *__restrict__ top_before,
+                               const int *__restrict__ flag_by_pre, const int *__restrict__ ntop_p,
+                               const float *__restrict__ box, const unsigned *__restrict__ slab,
+                               const unsigned *__restrict__ scene, float4 *__restrict__ nodes) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nn = 2 * n - 1;
-    if (x >= nn) return;
+    if (x >= n - 1) return;
     const int ntop = *ntop_p;
     auto final_id = [&](int y) {
         const int p = pre[y];
         return flag_by_pre[p] ? top_before[p] : ntop + (p - top_before[p]);
     };
-    // skip link: the sibling subtree of the nearest ancestor-or-self that is a first child
-    int c = x, skip = -1;
-    while (true) {
-        const int p = parent[c];
-        if (p < 0) break;
-        if (left[p] == c) {
-            skip = final_id(right[p]);
-            break;
-        }
-        c = p;
-    }
-    const int link = (x >= n - 1) ? ~(x - (n - 1)) : final_id(left[x]);
+    const float pad = 8.0e-6f * ord_flt(scene[6]) + 1e-30f;
     const int me = final_id(x);
-    const float *b = box + 6 * (size_t)x;
-    nodes[2 * (size_t)me] = make_float4(b[0], b[1], b[2], __int_as_float(skip));
-    nodes[2 * (size_t)me + 1] = make_float4(b[3], b[4], b[5], __int_as_float(link));
+    const int ch[2] = {left[x], right[x]};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const int y = ch[c];
+        const int ref = (y >= n - 1) ? ~(y - (n - 1)) : final_id(y);
+        const float *b = box + 9 * (size_t)y;
+        const unsigned umin = slab[2 * (size_t)y], umax = slab[2 * (size_t)y + 1];
+        float smin = -INFINITY, smax = INFINITY;
+        if (umin <= umax) { // extents were written (node within the slab limit)
+            smin = ord_flt(umin) - pad;
+            smax = ord_flt(umax) + pad;
+        }
+        nodes[6 * (size_t)me + 3 * c + 0] = make_float4(b[0], b[1], b[2], __int_as_float(ref));
+        nodes[6 * (size_t)me + 3 * c + 1] = make_float4(b[3], b[4], b[5], smin);
+        nodes[6 * (size_t)me + 3 * c + 2] = make_float4(b[6], b[7], b[8], smax);
+    }
 }
 
 } // namespace fluxb200

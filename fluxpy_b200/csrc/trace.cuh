@@ -108,93 +108,141 @@ __device__ __forceinline__ bool pluecker_hit(const Ray &r, float tnear, float tf
     return true;
 }
 
-// precomputed per-ray data of the (non-contract, conservative) box test
+// ---------------------------------------------------------------------------
+// BVH traversal.  NOT part of the arithmetic contract: it only has to be
+// conservative (never skip a triangle the Pluecker test would accept); which
+// triangles get tested is the only thing it decides.
+// ---------------------------------------------------------------------------
+constexpr int kStackDepth = 64;
+
+struct BvhView {
+    const float4 *nodes;  // global, 6 float4 per internal node (see lbvh.cuh flatten_kernel)
+    const float4 *top;    // shared-memory copy of the first ntop nodes (or nullptr)
+    const float4 *tri;    // 3 float4 per triangle, leaf order; tri[3k].w = face id bits
+    int ntop;
+    int ninternal;        // number of internal nodes (0: mesh with < 2 faces)
+    int nfaces;
+    int *error_flag;      // set to 1 on traversal stack overflow
+};
+
+// per-ray constants of the box / slab tests
 struct RayBox {
-    float ix, iy, iz; // 1/d with |d| clamped away from zero
+    float ix, iy, iz;    // 1/d, |d| clamped away from zero
+    float ox, oy, oz;    // o/d
 };
 __device__ __forceinline__ RayBox make_raybox(const Ray &r) {
     auto inv = [](float d) {
         const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
         return 1.0f / a;
     };
-    return RayBox{inv(r.dx), inv(r.dy), inv(r.dz)};
+    RayBox rb;
+    rb.ix = inv(r.dx);
+    rb.iy = inv(r.dy);
+    rb.iz = inv(r.dz);
+    rb.ox = r.ox * rb.ix;
+    rb.oy = r.oy * rb.iy;
+    rb.oz = r.oz * rb.iz;
+    return rb;
 }
 
-// slab test on [0, tmax]; boxes are padded at build time, the comparison has
-// one more relative guard band
-__device__ __forceinline__ bool box_hit(const Ray &r, const RayBox &rb, const float4 &a, const float4 &b,
-                                        float tmax) {
-    const float x0 = (a.x - r.ox) * rb.ix, x1 = (b.x - r.ox) * rb.ix;
-    const float y0 = (a.y - r.oy) * rb.iy, y1 = (b.y - r.oy) * rb.iy;
-    const float z0 = (a.z - r.oz) * rb.iz, z1 = (b.z - r.oz) * rb.iz;
-    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
-    return tn <= tf * 1.000001f;
+// child = (a: lo.xyz | ref) (b: hi.xyz | slab_min) (c: slab_dir.xyz | slab_max)
+// AABB slab test on [0, tmax] intersected with the fitted-slab interval.  Boxes
+// and slab extents are padded at build time; the final comparison carries one
+// more relative + absolute guard band.
+__device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const float4 &a, const float4 &b,
+                                          const float4 &c, float tmax) {
+    const float x0 = fmaf(a.x, rb.ix, -rb.ox), x1 = fmaf(b.x, rb.ix, -rb.ox);
+    const float y0 = fmaf(a.y, rb.iy, -rb.oy), y1 = fmaf(b.y, rb.iy, -rb.oy);
+    const float z0 = fmaf(a.z, rb.iz, -rb.oz), z1 = fmaf(b.z, rb.iz, -rb.oz);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+    // fitted slab: smin <= n.(o + t d) <= smax
+    const float no = fmaf(c.x, r.ox, fmaf(c.y, r.oy, c.z * r.oz));
+    const float nd = fmaf(c.x, r.dx, fmaf(c.y, r.dy, c.z * r.dz));
+    const float rn = 1.0f / nd; // +-inf when the ray runs parallel to the slab: see below
+    const float s0 = (b.w - no) * rn, s1 = (c.w - no) * rn;
+    // parallel ray: (b.w-no), (c.w-no) of opposite sign -> (-inf, +inf), no clipping;
+    // same sign -> both +inf or both -inf -> empty.  NaN (0*inf) is dropped by fmin/fmax.
+    tn = fmaxf(tn, fminf(s0, s1));
+    tf = fminf(tf, fmaxf(s0, s1));
+    return tn <= fmaf(tf, 1.000002f, 1e-30f);
 }
 
-struct BvhView {
-    const float4 *nodes;  // global, 2 float4 per node
-    const float4 *top;    // shared-memory copy of the first ntop nodes (or nullptr)
-    const float4 *tri;    // 3 float4 per triangle, leaf order; tri[3k].w = face id bits
-    int ntop;
-    int nnodes;
-};
-
-__device__ __forceinline__ void load_node(const BvhView &bvh, int node, float4 &a, float4 &b) {
+__device__ __forceinline__ void load_node(const BvhView &bvh, int node, float4 (&q)[6]) {
+    const float4 *p = (node < bvh.ntop) ? bvh.top + 6 * node : bvh.nodes + 6 * (size_t)node;
     if (node < bvh.ntop) {
-        a = bvh.top[2 * node];
-        b = bvh.top[2 * node + 1];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] = p[k];
     } else {
-        a = __ldg(bvh.nodes + 2 * (size_t)node);
-        b = __ldg(bvh.nodes + 2 * (size_t)node + 1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) q[k] = __ldg(p + k);
     }
 }
 
-// Any triangle k != target that the ray hits with 0 <= t_k and
-// (t_k < tlimit, or t_k == tlimit and face(k) > target_face)?  With
-// tlimit = t of the target triangle this is "closest hit != target" of the
+// exact test of one candidate triangle (leaf position `leaf`) for the occlusion
+// question "hit with 0 <= t and (t < tlimit, or t == tlimit and face > target_face)"
+__device__ __forceinline__ bool leaf_occludes(const BvhView &bvh, const Ray &r, float tlimit, int leaf,
+                                              int target_face) {
+    const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
+    const float4 p1 = __ldg(bvh.tri + 3 * (size_t)leaf + 1);
+    const float4 p2 = __ldg(bvh.tri + 3 * (size_t)leaf + 2);
+    float t;
+    if (!pluecker_hit(r, 0.0f, tlimit, p0, p1, p2, t)) return false;
+    return t < tlimit || __float_as_int(p0.w) > target_face;
+}
+
+// Generic any-hit traversal with immediate leaf tests (query kernels).
+// With tlimit = t of the target triangle this is "closest hit != target" of the
 // oracle's index-ordered closest-hit definition.  tlimit = +inf, target_leaf =
 // -1: plain occlusion query.
 __device__ __forceinline__ bool occluded_anyhit(const BvhView &bvh, const Ray &r, float tlimit,
                                                 int target_leaf, int target_face) {
-    if (bvh.nnodes == 0) return false;
+    if (bvh.nfaces == 0) return false;
+    if (bvh.ninternal == 0) // single triangle
+        return target_leaf != 0 && leaf_occludes(bvh, r, tlimit, 0, target_face);
     const RayBox rb = make_raybox(r);
-    const float tmax = tlimit * 1.000001f;
-    int node = 0;
-    while (node >= 0) {
-        float4 a, b;
-        load_node(bvh, node, a, b);
-        const int skip = __float_as_int(a.w), link = __float_as_int(b.w);
-        if (box_hit(r, rb, a, b, tmax)) {
-            if (link < 0) {
-                const int leaf = ~link;
-                if (leaf != target_leaf) {
-                    const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
-                    const float4 p1 = __ldg(bvh.tri + 3 * (size_t)leaf + 1);
-                    const float4 p2 = __ldg(bvh.tri + 3 * (size_t)leaf + 2);
-                    float t;
-                    if (pluecker_hit(r, 0.0f, tlimit, p0, p1, p2, t)) {
-                        if (t < tlimit || __float_as_int(p0.w) > target_face) return true;
-                    }
+    const float tmax = tlimit * 1.000002f;
+    int stack[kStackDepth];
+    int sp = 0, node = 0;
+    while (true) {
+        float4 q[6];
+        load_node(bvh, node, q);
+        int next = -1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (child_hit(r, rb, q[3 * c], q[3 * c + 1], q[3 * c + 2], tmax)) {
+                const int ref = __float_as_int(q[3 * c].w);
+                if (ref < 0) {
+                    const int leaf = ~ref;
+                    if (leaf != target_leaf && leaf_occludes(bvh, r, tlimit, leaf, target_face)) return true;
+                } else if (next < 0) {
+                    next = ref;
+                } else if (sp < kStackDepth) {
+                    stack[sp++] = ref;
+                } else {
+                    *bvh.error_flag = 1;
                 }
-                node = skip;
-            } else {
-                node = link;
             }
-        } else {
-            node = skip;
         }
+        if (next < 0) {
+            if (sp == 0) return false;
+            next = stack[--sp];
+        }
+        node = next;
     }
-    return false;
 }
 
 // visibility of target triangle (leaf position tleaf, face id tface) along ray r
-__device__ __forceinline__ bool target_visible(const BvhView &bvh, const Ray &r, int tleaf, int tface) {
+__device__ __forceinline__ bool target_hit_t(const BvhView &bvh, const Ray &r, int tleaf, float &tj) {
     const float4 p0 = __ldg(bvh.tri + 3 * (size_t)tleaf);
     const float4 p1 = __ldg(bvh.tri + 3 * (size_t)tleaf + 1);
     const float4 p2 = __ldg(bvh.tri + 3 * (size_t)tleaf + 2);
+    return pluecker_hit(r, 0.0f, __int_as_float(0x7f800000), p0, p1, p2, tj);
+}
+
+__device__ __forceinline__ bool target_visible(const BvhView &bvh, const Ray &r, int tleaf, int tface) {
     float tj;
-    if (!pluecker_hit(r, 0.0f, __int_as_float(0x7f800000), p0, p1, p2, tj)) return false;
+    if (!target_hit_t(bvh, r, tleaf, tj)) return false;
     return !occluded_anyhit(bvh, r, tj, tleaf, tface);
 }
 
@@ -218,29 +266,45 @@ __device__ __forceinline__ bool target_visible_bruteforce(const float4 *tri, int
 // closest hit (index-ordered definition) for intersect1
 __device__ __forceinline__ bool closest_hit(const BvhView &bvh, const Ray &r, float &t_best, int &face) {
     face = -1;
-    if (bvh.nnodes == 0) return false;
+    if (bvh.nfaces == 0) return false;
+    auto try_leaf = [&](int leaf) {
+        const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
+        float t;
+        if (pluecker_hit(r, 0.0f, t_best, p0, __ldg(bvh.tri + 3 * (size_t)leaf + 1),
+                         __ldg(bvh.tri + 3 * (size_t)leaf + 2), t)) {
+            const int f = __float_as_int(p0.w);
+            if (t < t_best || face < 0 || f > face) {
+                t_best = t;
+                face = f;
+            }
+        }
+    };
+    if (bvh.ninternal == 0) {
+        try_leaf(0);
+        return face >= 0;
+    }
     const RayBox rb = make_raybox(r);
-    int node = 0;
-    while (node >= 0) {
-        float4 a, b;
-        load_node(bvh, node, a, b);
-        const int skip = __float_as_int(a.w), link = __float_as_int(b.w);
-        if (box_hit(r, rb, a, b, t_best * 1.000001f)) {
-            if (link < 0) {
-                const int leaf = ~link;
-                const float4 p0 = __ldg(bvh.tri + 3 * (size_t)leaf);
-                float t;
-                if (pluecker_hit(r, 0.0f, t_best, p0, __ldg(bvh.tri + 3 * (size_t)leaf + 1),
-                                 __ldg(bvh.tri + 3 * (size_t)leaf + 2), t)) {
-                    const int f = __float_as_int(p0.w);
-                    if (t < t_best || face < 0 || f > face) {
-                        t_best = t;
-                        face = f;
-                    }
-                }
-                node = skip;
-            } else node = link;
-        } else node = skip;
+    int stack[kStackDepth];
+    int sp = 0, node = 0;
+    while (true) {
+        float4 q[6];
+        load_node(bvh, node, q);
+        int next = -1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (child_hit(r, rb, q[3 * c], q[3 * c + 1], q[3 * c + 2], t_best * 1.000002f)) {
+                const int ref = __float_as_int(q[3 * c].w);
+                if (ref < 0) try_leaf(~ref);
+                else if (next < 0) next = ref;
+                else if (sp < kStackDepth) stack[sp++] = ref;
+                else *bvh.error_flag = 1;
+            }
+        }
+        if (next < 0) {
+            if (sp == 0) break;
+            next = stack[--sp];
+        }
+        node = next;
     }
     return face >= 0;
 }

@@ -337,7 +337,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
 
     def bvh_export(self):
         info = self.bvh_info()
-        nodes = np.zeros((info.num_nodes, 8), np.float32)
+        nodes = np.zeros((info.num_nodes, 24), np.float32)
         leaf_face = np.zeros(self._nf, np.int32)
         _lib.check(_lib.lib().fluxb200_bvh_export(self._handle, _lib.ptr(nodes), _lib.ptr(leaf_face)))
         return nodes, leaf_face

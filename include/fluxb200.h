@@ -58,7 +58,7 @@ typedef struct fluxb200_ff_stats {
 
 typedef struct fluxb200_bvh_info {
     int64_t num_faces;
-    int64_t num_nodes;     /* 2*num_faces - 1 */
+    int64_t num_nodes;     /* internal (two-child) nodes: num_faces - 1 */
     int32_t num_top_nodes; /* nodes staged in shared memory by the trace kernel */
     int32_t max_depth;
     float ms_build;        /* device time of the last LBVH build */
@@ -96,8 +96,10 @@ int fluxb200_mesh_get_face_data(fluxb200_mesh *mesh, void *P, void *N, void *A);
  * once by fluxb200_mesh_create; exported so it can be timed. */
 int fluxb200_bvh_build(fluxb200_mesh *mesh);
 int fluxb200_bvh_info_get(fluxb200_mesh *mesh, fluxb200_bvh_info *info);
-/* Debug/test export of the flattened tree: nodes = num_nodes x 8 floats
- * (lo.xyz, skip-as-int-bits, hi.xyz, link-as-int-bits), leaf_face = nf int32. */
+/* Debug/test export of the flattened tree: nodes = num_nodes x 24 floats, two
+ * children of 12 floats each: (lo.xyz, ref-as-int-bits, hi.xyz, slab_min,
+ * slab_dir.xyz, slab_max); ref >= 0 internal node, ref < 0 triangle ~ref in
+ * leaf order.  leaf_face = nf int32 (face id of every leaf position). */
 int fluxb200_bvh_export(fluxb200_mesh *mesh, float *nodes, int32_t *leaf_face);
 
 /* ---- get_form_factor_matrix (src/flux/form_factors.py:11-72) -------------- */
@@ -175,7 +177,8 @@ int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *st
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, so a
  * caller can bracket calls with its own events. */
 int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
-/* Tunables: "top_nodes" (BVH nodes staged in shared memory), "trace_mode"
+/* Tunables: "top_nodes" (BVH nodes staged in shared memory), "slab_limit"
+ * (largest subtree, in faces, that gets a fitted slab), "blocks_per_sm", "trace_mode"
  * (0 = per-ray stackless), "sub_rows" (rows per sub-slab of fluxb200_ff_assemble). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 

@@ -197,35 +197,51 @@ def test_edge_cases(mods):
 
 
 def test_bvh_structure(mods):
-    """Every leaf triangle lies inside all its ancestors' boxes; skip links walk
-    the whole tree exactly once."""
+    """Every triangle lies inside the box AND the fitted slab of each of its
+    ancestors' child entries; the child references reach every internal node
+    and every triangle exactly once."""
     V, F = mods['meshes'].gaussian_crater(40, 2, dtype=np.float32)
     sm = mods['shape'].CudaTrimeshShapeModel(V, F)
     nodes, leaf_face = sm.bvh_export()
     nf = sm.num_faces
-    assert sorted(leaf_face.tolist()) == list(range(nf))
-    skip = nodes[:, 3].view(np.int32)
-    link = nodes[:, 7].view(np.int32)
-    # full traversal: always descend
-    seen, node, leaves = 0, 0, []
-    while node >= 0:
-        seen += 1
-        if link[node] < 0:
-            leaves.append(~link[node])
-            node = skip[node]
-        else:
-            node = link[node]
-    assert seen == 2*nf - 1 and sorted(leaves) == list(range(nf))
-    # containment of each triangle in its leaf box and in the root box
-    tri = V[F[leaf_face]]                       # (nf, 3, 3) in leaf order
-    leaf_nodes = np.where(link < 0)[0]
-    order = ~link[leaf_nodes]
-    lo, hi = nodes[leaf_nodes, 0:3], nodes[leaf_nodes, 4:7]
-    t = tri[order]
-    assert (t.min(1) >= lo).all() and (t.max(1) <= hi).all()
-    assert (V.min(0) >= nodes[0, 0:3]).all() and (V.max(0) <= nodes[0, 4:7]).all()
+    assert sorted(leaf_face.tolist()) == list(range(nf)) and nodes.shape == (nf - 1, 24)
+    tri = V[F[leaf_face]].astype(np.float64)            # (nf, 3, 3) in leaf order
+    ref = np.ascontiguousarray(nodes[:, [3, 15]]).view(np.int32)
+    seen_nodes = set()
+
+    def leaves_under(r):                                 # iterative DFS, returns leaf positions
+        out, stack = [], [r]
+        while stack:
+            x = stack.pop()
+            if x < 0:
+                out.append(~x)
+            else:
+                assert x not in seen_nodes
+                seen_nodes.add(x)
+                stack += [int(ref[x, 0]), int(ref[x, 1])]
+        return out
+
+    seen_leaves = leaves_under(0)
+    assert len(seen_nodes) == nf - 1 and sorted(seen_leaves) == list(range(nf))
+    finite_slabs = 0
+    for x in range(nf - 1):
+        for c in range(2):
+            e = nodes[x, 12*c:12*c + 12].astype(np.float64)
+            lo, hi, smin, d, smax = e[0:3], e[4:7], e[7], e[8:11], e[11]
+            r = int(ref[x, c])
+            if r >= 0 and x % 37:                        # full subtree check on a subset (cost)
+                continue
+            seen_nodes.clear()
+            lv = leaves_under(r)
+            t = tri[lv].reshape(-1, 3)
+            assert (t >= lo).all() and (t <= hi).all()
+            proj = t@d
+            assert (proj >= smin).all() and (proj <= smax).all()
+            assert abs(np.linalg.norm(d) - 1) < 1e-5
+            finite_slabs += np.isfinite(smin)
+    assert finite_slabs > nf//2
     info = sm.bvh_info()
-    assert info.num_nodes == 2*nf - 1 and 0 < info.num_top_nodes <= 1024
+    assert info.num_nodes == nf - 1 and 0 < info.num_top_nodes <= 256
 
 
 @pytest.mark.parametrize('dtype', [np.float32])

@@ -29,5 +29,10 @@ if __name__ == '__main__':
     run(317, 4096)
     run(317, 4096, np.float64)
     run(317, 4096, opts=(('top_nodes', 0),))
-    run(317, 4096, opts=(('top_nodes', 4096),))
+    run(317, 4096, opts=(('top_nodes', 1024),))
+    run(317, 4096, opts=(('slab_limit', 0),))
+    run(317, 4096, opts=(('slab_limit', 256),))
+    run(317, 4096, opts=(('slab_limit', 65536),))
+    run(317, 4096, opts=(('blocks_per_sm', 2),))
+    run(317, 4096, opts=(('blocks_per_sm', 4),))
     run(501, 2048)

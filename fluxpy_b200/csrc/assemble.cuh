@@ -83,15 +83,17 @@ constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 //            and are Pluecker-tested in a converged loop; occluded rays clear
 //            their bit in the warp's shared words;
 //   phase 3  the 32 final words go out as one coalesced 128-byte store.
-template <class T>
-__global__ void __launch_bounds__(kTraceThreads, 3) trace_kernel(const TraceArgs<T> A) {
+template <class T, bool kTop>
+__global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs<T> A) {
     extern __shared__ float4 smem_top[];
     __shared__ uint32_t words_s[kTraceWarps][32];
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-    for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
-    __syncthreads();
-    const BvhView bvh{A.nodes, smem_top, A.tri, A.ntop, A.ninternal, A.nfaces, A.error_flag};
+    if (kTop) {
+        for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
+        __syncthreads();
+    }
+    const BvhView bvh{A.nodes, smem_top, A.tri, kTop ? A.ntop : 0, A.ninternal, A.nfaces, A.error_flag};
     const unsigned total_units = (unsigned)A.m * (unsigned)A.nchunks;
     unsigned long long tested = 0;
 
@@ -172,31 +174,23 @@ __global__ void __launch_bounds__(kTraceThreads, 3) trace_kernel(const TraceArgs
                 nl = 0;
                 if (blocked) active = false;
             };
+            // (the tree depth was checked against kStackDepth when it was built)
             while (__any_sync(0xffffffffu, active)) {
                 if (active) {
                     float4 q[6];
-                    load_node(bvh, node, q);
-                    int next = -1;
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        if (child_hit(ray, rb, q[3 * ch], q[3 * ch + 1], q[3 * ch + 2], tmax)) {
-                            const int ref = __float_as_int(q[3 * ch].w);
-                            if (ref < 0) {
-                                if (~ref != tleaf) leaf_s[nl++][tid] = ~ref;
-                            } else if (next < 0) {
-                                next = ref;
-                            } else if (sp < kStackDepth) {
-                                stack[sp++] = ref;
-                            } else {
-                                *A.error_flag = 1;
-                            }
-                        }
+                    load_node<kTop>(bvh, node, q);
+                    const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
+                    const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
+                    const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                    if (h0 && r0 < 0 && ~r0 != tleaf) leaf_s[nl++][tid] = ~r0;
+                    if (h1 && r1 < 0 && ~r1 != tleaf) leaf_s[nl++][tid] = ~r1;
+                    const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
+                    if (i0 && i1) stack[sp++] = r1;
+                    node = i0 ? r0 : r1;
+                    if (!(i0 || i1)) {
+                        if (sp > 0) node = stack[--sp];
+                        else active = false;
                     }
-                    if (next < 0) {
-                        if (sp == 0) active = false;
-                        else next = stack[--sp];
-                    }
-                    node = next;
                 }
                 if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
             }

@@ -33,9 +33,9 @@ struct fluxb200_mesh {
         scene, scalars, nodes, tri, face_leaf;
     RadixSorter sorter;
     int nnodes = 0, ninternal = 0, ntop = 0, max_depth = 0;
-    int top_nodes_opt = 256;
-    int slab_limit_opt = 4096;
-    int blocks_per_sm = 3;
+    int top_nodes_opt = 0;   // measured: L1 already serves the top of the tree (profiles/)
+    int slab_limit_opt = 1 << 30;
+    int blocks_per_sm = 4;
     float ms_build = 0.f;
     float scene_h[7] = {};
 
@@ -44,9 +44,10 @@ struct fluxb200_mesh {
         counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout;
     // streaming assembly (double-buffered sub-slabs, second stream for fill + D2H)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t slot_free[2] = {};
+    static constexpr int kSlots = 3;
+    cudaEvent_t slot_free[kSlots] = {};
     std::vector<cudaEvent_t> sub_events;
-    DevBuf sbits[2], scounts[2], scounts64[2], sindptr[2], stage_data[2], stage_idx[2];
+    DevBuf sbits[kSlots], scounts[kSlots], scounts64[kSlots], sindptr[kSlots], stage_data[kSlots], stage_idx[kSlots];
     HostBuf h_nnz, h_counts;
     int64_t dev_capacity_hint = 0;
     int sub_rows_opt = 512;
@@ -341,13 +342,15 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
     FB_REQUIRE((int)smem + 16384 <= M->max_smem_optin, "top_nodes does not fit in shared memory");
-    FB_CUDA(cudaFuncSetAttribute(trace_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)std::max<size_t>(smem, 1024)));
+    if (M->ntop > 0)
+        FB_CUDA(cudaFuncSetAttribute(trace_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)std::max<size_t>(smem, 1024)));
     FB_CUDA(cudaMemsetAsync(M->tested.as<unsigned long long>() + 1, 0, sizeof(unsigned long long), st));
     const int64_t units = (int64_t)mr * A.nchunks;
     const int grid = (int)std::min<int64_t>((int64_t)M->num_sms * M->blocks_per_sm,
                                             std::max<int64_t>(1, ceil_div(units, kTraceWarps)));
-    trace_kernel<T><<<grid, kTraceThreads, smem, st>>>(A);
+    if (M->ntop > 0) trace_kernel<T, true><<<grid, kTraceThreads, smem, st>>>(A);
+    else trace_kernel<T, false><<<grid, kTraceThreads, 0, st>>>(A);
     FB_CUDA(cudaGetLastError());
 }
 
@@ -494,7 +497,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     const size_t sub = std::max<size_t>(1, std::min<size_t>((size_t)M->sub_rows_opt, std::max<size_t>(m, 1)));
     const size_t nsub = m ? (size_t)ceil_div((int64_t)m, (int64_t)sub) : 0;
     // per-slot (double-buffered) device state
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < fluxb200_mesh::kSlots; ++b) {
         M->sbits[b].reserve(sizeof(uint32_t) * sub * (size_t)std::max(M->nwords, 1));
         M->scounts[b].reserve(sizeof(uint32_t) * sub);
         M->scounts64[b].reserve(sizeof(int64_t) * sub);
@@ -523,9 +526,10 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     float ms_fill = 0.f;
 
     auto enqueue_trace = [&](size_t k) {
-        const int b = (int)(k & 1);
+        const int b = (int)(k % fluxb200_mesh::kSlots);
         const size_t row0 = k * sub, mr = std::min(sub, m - row0);
-        if (k >= 2) FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0)); // fill(k-2) done with slot b
+        if (k >= (size_t)fluxb200_mesh::kSlots)
+            FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0)); // fill(k - kSlots) is done with slot b
         FB_CUDA(cudaMemsetAsync(M->scounts[b].p, 0, sizeof(uint32_t) * mr, s0));
         FB_CUDA(cudaEventRecord(M->sub_events[3 * k], s0));
         if (n) launch_trace<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->scounts[b].as<uint32_t>(), s0);
@@ -541,7 +545,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         launches += (n ? 1 : 0) + 2;
     };
     auto finish = [&](size_t k) {
-        const int b = (int)(k & 1);
+        const int b = (int)(k % fluxb200_mesh::kSlots);
         const size_t row0 = k * sub, mr = std::min(sub, m - row0);
         FB_CUDA(cudaEventSynchronize(M->sub_events[3 * k + 2]));
         const int64_t nnz_k = h_nnz[k], off = total;
@@ -549,6 +553,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         if (index_width == 4 && total >= (1ll << 31)) throw CudaError{"int32 indices cannot hold this matrix"};
         if (total > capacity) overflow = true;
         FB_CUDA(cudaStreamWaitEvent(s1, M->sub_events[3 * k + 2], 0));
+        bool slot_recorded = false;
         if (!overflow && nnz_k) {
             T *d_data;
             void *d_idx;
@@ -567,6 +572,8 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
             launch_fill<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->sindptr[b].as<int64_t>(), base, d_data,
                            d_idx, index_width, s1);
             ++launches;
+            FB_CUDA(cudaEventRecord(M->slot_free[b], s1)); // bits / indptr of the slot are consumed
+            slot_recorded = true;
             if (destination == 0) {
                 FB_CUDA(cudaMemcpyAsync((char *)data + sizeof(T) * (size_t)off, d_data, sizeof(T) * (size_t)nnz_k,
                                         cudaMemcpyDeviceToHost, s1));
@@ -574,7 +581,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
                                         (size_t)index_width * (size_t)nnz_k, cudaMemcpyDeviceToHost, s1));
             }
         }
-        FB_CUDA(cudaEventRecord(M->slot_free[b], s1));
+        if (!slot_recorded) FB_CUDA(cudaEventRecord(M->slot_free[b], s1));
     };
 
     FB_CUDA(cudaEventRecord(M->ev[4], s1));
@@ -717,8 +724,11 @@ int fluxb200_mesh_create(const void *V, size_t nv, const int64_t *F, size_t nf, 
         M->dtype = dtype_code;
         M->nv = nv;
         M->nf = nf;
-        FB_CUDA(cudaStreamCreateWithFlags(&M->stream, cudaStreamNonBlocking));
-        FB_CUDA(cudaStreamCreateWithFlags(&M->copy_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        FB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        FB_CUDA(cudaStreamCreateWithPriority(&M->stream, cudaStreamNonBlocking, prio_lo));
+        // fill + copies run under the persistent trace kernel: let them win free CTA slots
+        FB_CUDA(cudaStreamCreateWithPriority(&M->copy_stream, cudaStreamNonBlocking, prio_hi));
         for (auto &e : M->slot_free) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : M->ev) FB_CUDA(cudaEventCreate(&e));
         FB_CUDA(cudaDeviceGetAttribute(&M->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -759,7 +769,7 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
                           &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};
         for (DevBuf *b : bufs) b->release();
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < fluxb200_mesh::kSlots; ++k) {
             M->sbits[k].release(); M->scounts[k].release(); M->scounts64[k].release(); M->sindptr[k].release();
             M->stage_data[k].release(); M->stage_idx[k].release();
             if (M->slot_free[k]) cudaEventDestroy(M->slot_free[k]);

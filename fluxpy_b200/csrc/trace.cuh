@@ -159,7 +159,8 @@ __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const 
     // fitted slab: smin <= n.(o + t d) <= smax
     const float no = fmaf(c.x, r.ox, fmaf(c.y, r.oy, c.z * r.oz));
     const float nd = fmaf(c.x, r.dx, fmaf(c.y, r.dy, c.z * r.dz));
-    const float rn = 1.0f / nd; // +-inf when the ray runs parallel to the slab: see below
+    float rn; // approximate reciprocal (MUFU.RCP): +-inf when the ray runs parallel to the slab
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nd));
     const float s0 = (b.w - no) * rn, s1 = (c.w - no) * rn;
     // parallel ray: (b.w-no), (c.w-no) of opposite sign -> (-inf, +inf), no clipping;
     // same sign -> both +inf or both -inf -> empty.  NaN (0*inf) is dropped by fmin/fmax.
@@ -168,12 +169,14 @@ __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const 
     return tn <= fmaf(tf, 1.000002f, 1e-30f);
 }
 
+template <bool kTop = true>
 __device__ __forceinline__ void load_node(const BvhView &bvh, int node, float4 (&q)[6]) {
-    const float4 *p = (node < bvh.ntop) ? bvh.top + 6 * node : bvh.nodes + 6 * (size_t)node;
-    if (node < bvh.ntop) {
+    if (kTop && node < bvh.ntop) { // staged in shared memory
+        const float4 *p = bvh.top + 6 * node;
 #pragma unroll
         for (int k = 0; k < 6; ++k) q[k] = p[k];
     } else {
+        const float4 *p = bvh.nodes + 6 * (size_t)node;
 #pragma unroll
         for (int k = 0; k < 6; ++k) q[k] = __ldg(p + k);
     }

@@ -262,8 +262,10 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
-    #: running estimate of nnz / (m*n), used to size the streaming output buffers
-    _fill_ratio = 0.6
+    #: largest nnz / (m*n) seen so far (slowly forgotten): sizes the streaming
+    #: output buffers, with 20 % headroom, so that a retry is the exception
+    _fill_ratio = 0.55
+    overflow_retries = 0
 
     def _ff_assemble_host(self, I, J, eps, want_row_counts=False):
         """Streaming assembly (``fluxb200_ff_assemble``) into page-locked host
@@ -278,7 +280,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         counts = np.empty(m, np.int64) if want_row_counts else None
         st = _lib.FFStats()
         esz = np.dtype(self.dtype).itemsize
-        cap = int(min(m*n, max(1024, self._fill_ratio*1.08*m*n + 4096)))
+        cap = int(min(m*n, max(1024, self._fill_ratio*1.2*m*n + 4096)))
         while True:
             idt = np.int32 if max(cap, n, m + 1) < 2**31 else np.int64
             isz = np.dtype(idt).itemsize
@@ -290,6 +292,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                                         _lib.ptr(counts), ctypes.byref(st))
             if rc == _lib.OVERFLOW:
                 _lib.arena.discard(block)
+                type(self).overflow_retries += 1
                 cap = int(st.nnz)
                 continue
             if rc:
@@ -298,7 +301,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             break
         nnz = int(st.nnz)
         if m*n:
-            type(self)._fill_ratio = max(0.02, nnz/(m*n))
+            type(self)._fill_ratio = max(0.02, nnz/(m*n), 0.98*self._fill_ratio)
         data, indices, indptr = _lib.arena.arrays(
             block, [(0, nnz, self.dtype), (off_idx, nnz, idt), (off_ptr, m + 1, idt)])
         return m, n, indptr, indices, data, counts, st

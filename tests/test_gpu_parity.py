@@ -241,7 +241,15 @@ def test_bvh_structure(mods):
             finite_slabs += np.isfinite(smin)
     assert finite_slabs > nf//2
     info = sm.bvh_info()
-    assert info.num_nodes == nf - 1 and 0 < info.num_top_nodes <= 256
+    assert info.num_nodes == nf - 1 and info.num_top_nodes == 0     # default: nothing staged in smem
+    # staging the top of the tree in shared memory / restricting the slabs changes no result
+    ref = mods['ff'].get_form_factor_matrix(sm)
+    for name, val in (('top_nodes', 64), ('top_nodes', 700), ('slab_limit', 16), ('slab_limit', 0),
+                      ('blocks_per_sm', 1)):
+        sm.set_option(name, val)
+        if name == 'top_nodes':
+            assert 0 < sm.bvh_info().num_top_nodes <= val
+        assert same_csr(mods['ff'].get_form_factor_matrix(sm), ref)
 
 
 @pytest.mark.parametrize('dtype', [np.float32])

@@ -23,16 +23,25 @@ def run(n, rows, dtype=np.float32, opts=()):
           f'wall={dt*1e3:.1f} ms  -> {st.pairs_tested/st.ms_trace/1e6:.3f} Grays/s, {st.pairs_all/(st.ms_trace+st2.ms_fill+st.ms_prepare+st.ms_scan)/1e6:.3f} Gpairs/s', flush=True)
 
 if __name__ == '__main__':
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'quick':
+        run(317, 4096)
+        run(317, 4096, opts=(('blocks_per_sm', 4),))
+        run(317, 4096, opts=(('top_nodes', 256),))
+        run(317, 4096, opts=(('slab_limit', 4096),))
+        run(159, 4096)
+        run(501, 2048)
+        sys.exit(0)
     run(72, None)
     run(159, 4096)
     run(317, 1024)
     run(317, 4096)
     run(317, 4096, np.float64)
-    run(317, 4096, opts=(('top_nodes', 0),))
+    run(317, 4096, opts=(('top_nodes', 256),))
     run(317, 4096, opts=(('top_nodes', 1024),))
     run(317, 4096, opts=(('slab_limit', 0),))
     run(317, 4096, opts=(('slab_limit', 256),))
-    run(317, 4096, opts=(('slab_limit', 65536),))
+    run(317, 4096, opts=(('slab_limit', 4096),))
     run(317, 4096, opts=(('blocks_per_sm', 2),))
     run(317, 4096, opts=(('blocks_per_sm', 4),))
     run(501, 2048)

@@ -137,3 +137,44 @@ def test_row_count_exchange_gloo(world, tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_install_into_reference_package():
+    """INTEGRATION.md section 1 against the real reference package, when it is
+    present (build container only; the GPU box has no /root/reference)."""
+    ref = '/root/reference/src'
+    if not os.path.isdir(ref):
+        pytest.skip('reference tree not present')
+    code = r'''
+import sys, types, functools
+cp = types.ModuleType('cached_property'); cp.cached_property = functools.cached_property
+sys.modules['cached_property'] = cp
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import flux.shape, flux.form_factors
+from fluxpy_b200 import integration, CudaTrimeshShapeModel
+orig = flux.form_factors.get_form_factor_matrix
+f = integration.install()
+assert flux.shape.trimesh_shape_models[-1] is CudaTrimeshShapeModel
+assert flux.form_factors.get_form_factor_matrix is f and f is not orig
+integration.install()                                   # idempotent
+assert flux.shape.trimesh_shape_models.count(CudaTrimeshShapeModel) == 1
+# a non-CUDA model still goes to the reference implementation
+class Dummy: pass
+try:
+    f(Dummy())
+except AttributeError:
+    pass
+else:
+    raise SystemExit('reference path not taken')
+# same public surface as the reference's shape model
+import inspect
+for name in ('get_visibility', 'get_visibility_1_to_N', 'get_visibility_matrix', 'is_occluded',
+             'intersect1', 'get_direct_irradiance', 'num_faces', 'num_verts'):
+    assert hasattr(CudaTrimeshShapeModel, name), name
+a = inspect.signature(flux.shape.TrimeshShapeModel.__init__)
+b = inspect.signature(CudaTrimeshShapeModel.__init__)
+assert list(a.parameters) == list(b.parameters)
+print('ok')
+''' % (ROOT, ref)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and 'ok' in out.stdout, out.stdout + out.stderr

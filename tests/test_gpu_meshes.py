@@ -1,0 +1,189 @@
+"""GPU tier, other geometry classes of BASELINE.json's configs: closed body with
+heavy self-occlusion (config 4), float64 planetocentric coordinates (config 3
+variant), Ingersoll bowl (config 1), coincident faces (closest-hit
+tie rule), random triangle soup (conservativeness of the box + slab tests).
+Everything is compared bit for bit with the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import fluxpy_b200
+    from fluxpy_b200 import meshes, shape, form_factors
+    from oracle import oracle
+    return dict(pkg=fluxpy_b200, meshes=meshes, shape=shape, ff=form_factors, oracle=oracle)
+
+
+def same_csr(A, B):
+    A.sort_indices()
+    B.sort_indices()
+    return (A.shape == B.shape and np.array_equal(A.indptr, B.indptr)
+            and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data))
+
+
+def both(mods, V, F, N=None):
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, None if N is None else N.copy())
+    om = mods['oracle'].OracleShapeModel(V, F, N=None if N is None else N.copy())
+    return sm, om
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_closed_cratered_body_small(mods, dtype):
+    """Ceres stand-in at 5 120 faces, outward normals: most cull survivors are occluded."""
+    V, F = mods['meshes'].cratered_body(subdiv=4, ncraters=60, seed=0, dtype=dtype)
+    sm, om = both(mods, V, F)
+    assert ((sm.P*sm.N).sum(1) > 0).mean() > 0.99          # outward
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    st = dict(mods['ff'].last_stats)
+    FO, so = mods['oracle'].get_form_factor_matrix(om, return_stats=True)
+    assert same_csr(FF, FO) and st['pairs_tested'] == so['pairs_tested']
+    assert 0 < FF.nnz < st['pairs_tested']                 # real occlusion happened
+    nf = sm.num_faces
+    I = np.arange(0, nf, 7)
+    vis = sm._get_visibility(I, np.arange(nf))
+    assert (vis == sm._get_visibility(I, np.arange(nf), _bruteforce=True)).all()
+    vo = om.get_visibility(I, np.arange(nf))
+    vo[np.arange(len(I)), I] = False
+    assert (vis == vo).all()
+    rng = np.random.default_rng(0)
+    D = rng.normal(size=(5, 3)).astype(dtype)
+    D /= np.linalg.norm(D, axis=1)[:, None]
+    for d in D:
+        assert (sm.is_occluded(np.arange(nf), d) == om.is_occluded(np.arange(nf), d)).all()
+    # extended source: all directions for every face (CGAL 2-D variant, aabb.pyx:77-87)
+    occ2 = sm.is_occluded(np.arange(nf), D)
+    assert occ2.shape == (nf, 5)
+    for k in range(5):
+        assert (occ2[:, k] == om.is_occluded(np.arange(nf), D[k])).all()
+    E = sm.get_direct_irradiance(1365.0, D)
+    assert E.shape == (nf,) and (E >= 0).all()
+
+
+def test_closed_cratered_body_82k_sampled_rows(mods):
+    """Config 4 size: 81 920 faces; sampled rows against the oracle."""
+    V, F = mods['meshes'].cratered_body(subdiv=6, seed=0, dtype=np.float32)
+    sm, om = both(mods, V, F)
+    rows = np.array([0, 1234, 40000, 81919, 60001, 7])
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, rows),
+                    mods['oracle'].get_form_factor_matrix(om, rows))
+    st = dict(mods['ff'].last_stats)
+    assert 0 < st['nnz'] < st['pairs_tested']
+
+
+def test_float64_planetocentric_coordinates(mods):
+    """Gerlache-like: metres, Moon-centred (|p| ~ 1.7e6), float64 model.  The
+    ray tracer works on the float32 copy of the vertices exactly as Embree's
+    vertex buffer does (shape.py:319-325); numerators are evaluated directly so
+    they do not cancel."""
+    V, F = mods['meshes'].gaussian_crater(48, 3, dtype=np.float64, scale=20e3, offset=(0., 0., -1.7374e6))
+    N = mods['meshes'].upward_normals(V, F)
+    sm, om = both(mods, V, F, N)
+    FF = mods['ff'].get_form_factor_matrix(sm, eps=1e-5)
+    FO = mods['oracle'].get_form_factor_matrix(om, eps=1e-5)
+    assert same_csr(FF, FO) and FF.dtype == np.float64 and FF.nnz > 0
+    # 1e-12 against the float64 ground truth on the stored entries.  eps is dimensionful
+    # (SURVEY P3): in metres it lets pairs with cos ~ 1e-9 through, whose value no float64
+    # evaluation can give to 1e-12 -- the bound carries the condition number |d|/(n.d)
+    num, val = mods['oracle'].form_factor_dense_f64(sm.P, sm.N, sm.A)
+    D = FF.toarray()
+    m = D != 0
+    P64 = sm.P.astype(np.float64)
+    d = P64[None, :, :] - P64[:, None, :]
+    dn = np.sqrt((d*d).sum(-1))
+    a = np.abs(np.einsum('ik,ijk->ij', sm.N, d))
+    b = np.abs(np.einsum('jk,ijk->ij', sm.N, d))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        cond = dn/a + dn/b
+    tol = 1e-12 + 8*2.0**-53*cond
+    assert (np.abs(D[m] - val[m]) <= tol[m]*np.abs(val[m])).all()
+    assert (cond[m] < 1e3).mean() > 0.5        # and for most entries that IS 1e-12
+    nf = sm.num_faces
+    I = np.arange(0, nf, 11)
+    assert (sm._get_visibility(I, np.arange(nf)) == sm._get_visibility(I, np.arange(nf), _bruteforce=True)).all()
+
+
+def test_ingersoll_bowl(mods):
+    """Config 1 stand-in: exactly flat plane faces cull to nothing, faces inside
+    the spherical cap see each other (concave), block == slice."""
+    V, F = mods['meshes'].ingersoll_bowl(41, dtype=np.float64)
+    N = mods['meshes'].upward_normals(V, F)
+    sm, om = both(mods, V, F, N)
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    assert same_csr(FF, mods['oracle'].get_form_factor_matrix(om))
+    flat = np.abs(V[F][:, :, 2]).max(1) == 0
+    rc = np.diff(FF.indptr)
+    assert flat.any() and (rc[flat] == 0).all()
+    inner = (np.linalg.norm(sm.P[:, :2], axis=1) < 0.6)
+    sub = FF[inner, :][:, inner].toarray()
+    Pin = sm.P[inner]
+    far = np.linalg.norm(Pin[:, None] - Pin[None], axis=2) > 0.3   # near neighbours fall under eps
+    assert (sub != 0)[far].all()
+    # the spherical-cap identity: inside a sphere the point kernel is 1/(4 pi R^2)
+    R = 0.8/np.sin(np.deg2rad(40.0))
+    i, j = np.where(inner)[0][[3, -5]]
+    assert abs(FF[i, j]/sm.A[j] - 1/(4*np.pi*R*R)) < 0.05/(4*np.pi*R*R)
+
+
+def test_coincident_faces_tie_rule(mods):
+    """Two copies of the same triangle have the same hit distance: the oracle's
+    index-ordered closest hit keeps the later one.  The CUDA any-hit form must
+    agree (t_k == t_j and k > j occludes j)."""
+    V, F = mods['meshes'].gaussian_crater(14, 5, dtype=np.float32)
+    dup = np.arange(40, 80)
+    F2 = np.vstack([F, F[dup]])                      # faces 40..79 exist twice
+    N = mods['meshes'].upward_normals(V, F2)
+    sm, om = both(mods, V, F2, N)
+    FF = mods['ff'].get_form_factor_matrix(sm)
+    assert same_csr(FF, mods['oracle'].get_form_factor_matrix(om))
+    nf0 = len(F)
+    D = FF.toarray()
+    # the earlier copy is hidden behind the later copy for every source that sees the pair
+    seen_late = (D[:, nf0:nf0 + len(dup)] != 0)
+    seen_early = (D[:, dup] != 0)
+    assert seen_late.any() and not (seen_early & seen_late).any()
+
+
+def test_random_triangle_soup(mods):
+    """No surface structure at all: exercises the conservativeness of the padded
+    boxes and fitted slabs (BVH == brute force == oracle)."""
+    rng = np.random.default_rng(11)
+    nt = 1500
+    c = rng.uniform(-1, 1, (nt, 1, 3))
+    V = (c + rng.normal(scale=0.08, size=(nt, 3, 3))).reshape(-1, 3).astype(np.float32)
+    F = np.arange(3*nt).reshape(nt, 3)
+    sm, om = both(mods, V, F)
+    I = np.arange(nt)
+    vis = sm._get_visibility(I, I)
+    assert (vis == sm._get_visibility(I, I, _bruteforce=True)).all()
+    vo = om.get_visibility_matrix()
+    vo[I, I] = False
+    assert (vis == vo).all() and 0.05 < vis.mean() < 0.95
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, eps=1e-7),
+                    mods['oracle'].get_form_factor_matrix(om, eps=1e-7))
+    d = np.array([0.2, -0.3, 0.9], np.float32)
+    assert (sm.is_occluded(I, d) == om.is_occluded(I, d)).all()
+    hit = sm.intersect1(np.array([0., 0., 5.]), np.array([0., 0., -1.]))
+    assert hit is None or (0 <= hit[0] < nt)
+
+
+def test_full_50k_matrix_properties(mods):
+    """BASELINE config 2 size (G(159,0), 49 928 faces): the whole 2.5e9-pair
+    matrix, device-resident; counts are consistent with a second, differently
+    split assembly; sampled rows equal the oracle."""
+    V, F = mods['meshes'].gaussian_crater(159, 0, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm, om = both(mods, V, F, N)
+    nf = sm.num_faces
+    m, n, counts, st = sm._ff_assemble_device(None, None, 1e-5, 4, want_row_counts=True)
+    assert m == n == nf and counts.sum() == st.nnz and st.pairs_all == nf*nf
+    assert 0.3*nf*nf < st.nnz <= st.pairs_tested
+    sm.set_option('sub_rows', 3000)
+    m2, n2, counts2, st2 = sm._ff_assemble_device(None, None, 1e-5, 4, want_row_counts=True)
+    assert np.array_equal(counts, counts2) and st2.pairs_tested == st.pairs_tested
+    rows = np.array([5, 25000, 49927])
+    FO = mods['oracle'].get_form_factor_matrix(om, rows)
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, rows), FO)
+    assert np.array_equal(np.diff(FO.indptr), counts[rows])

@@ -263,13 +263,15 @@ def main():
         chk = float(FF.data[:16].sum())                  # touch the result on the host
         return st, h2d, d2h, chk
 
-    for s in range(min(args.warmup, 2)):
+    for s in range(args.warmup):
         step_e2e(s)
     barrier()
     t0 = time.perf_counter()
-    e2e = {'tested': 0, 'h2d': 0, 'd2h': 0}
+    e2e = {'tested': 0, 'h2d': 0, 'd2h': 0, 'step_ms': []}
     for s in range(args.warmup, args.warmup + args.steps):
+        ts = time.perf_counter()
         st, h2d, d2h, _ = step_e2e(s)
+        e2e['step_ms'].append(round(1e3*(time.perf_counter() - ts), 2))
         e2e['tested'] += st['pairs_tested']
         e2e['h2d'] += h2d
         e2e['d2h'] += d2h
@@ -350,7 +352,8 @@ def main():
             'clocks': clocks,
             'e2e': {'value': e2e_tested_all/t_e2e_max, 'unit': 'pairs/s',
                     'h2d_bytes_per_step': e2e['h2d']/steps, 'd2h_bytes_per_step': e2e['d2h']/steps,
-                    'ms_per_step': 1e3*t_e2e_max/steps},
+                    'ms_per_step': 1e3*t_e2e_max/steps, 'step_ms_rank0': e2e['step_ms'],
+                    'output_buffer_retries': fluxpy_b200.CudaTrimeshShapeModel.overflow_retries},
             'gpu_launches': int(launches_all),
             'roofline': roof,
             'cpu_baseline': cpu,

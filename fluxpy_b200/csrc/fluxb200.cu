@@ -495,7 +495,22 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     int launches = prepare_call<T>(M, I, m, J, n, eps);
     FB_CUDA(cudaEventRecord(M->ev[1], s0));
     const size_t sub = std::max<size_t>(1, std::min<size_t>((size_t)M->sub_rows_opt, std::max<size_t>(m, 1)));
-    const size_t nsub = m ? (size_t)ceil_div((int64_t)m, (int64_t)sub) : 0;
+    // sub-slab boundaries: full-size pieces, then a geometrically shrinking tail so that the last
+    // fill + copy-out (which no tracing overlaps) is short
+    std::vector<size_t> bounds{0};
+    {
+        size_t pos = 0;
+        const size_t min_piece = std::max<size_t>(32, sub / 8);
+        while (pos < m) {
+            const size_t rem = m - pos;
+            size_t piece = sub;
+            if (destination == 0 && rem <= 2 * sub) piece = std::max(min_piece, (rem + 1) / 2);
+            piece = std::min(piece, rem);
+            pos += piece;
+            bounds.push_back(pos);
+        }
+    }
+    const size_t nsub = bounds.size() - 1;
     // per-slot (double-buffered) device state
     for (int b = 0; b < fluxb200_mesh::kSlots; ++b) {
         M->sbits[b].reserve(sizeof(uint32_t) * sub * (size_t)std::max(M->nwords, 1));
@@ -527,7 +542,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
 
     auto enqueue_trace = [&](size_t k) {
         const int b = (int)(k % fluxb200_mesh::kSlots);
-        const size_t row0 = k * sub, mr = std::min(sub, m - row0);
+        const size_t row0 = bounds[k], mr = bounds[k + 1] - row0;
         if (k >= (size_t)fluxb200_mesh::kSlots)
             FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0)); // fill(k - kSlots) is done with slot b
         FB_CUDA(cudaMemsetAsync(M->scounts[b].p, 0, sizeof(uint32_t) * mr, s0));
@@ -546,7 +561,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     };
     auto finish = [&](size_t k) {
         const int b = (int)(k % fluxb200_mesh::kSlots);
-        const size_t row0 = k * sub, mr = std::min(sub, m - row0);
+        const size_t row0 = bounds[k], mr = bounds[k + 1] - row0;
         FB_CUDA(cudaEventSynchronize(M->sub_events[3 * k + 2]));
         const int64_t nnz_k = h_nnz[k], off = total;
         total += nnz_k;
@@ -585,11 +600,14 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     };
 
     FB_CUDA(cudaEventRecord(M->ev[4], s1));
+    // The persistent trace kernel owns every CTA slot while it runs, so fill(k) is put on the
+    // (higher-priority) copy stream BEFORE trace(k+1) is submitted: the fill takes the idle
+    // machine first, trace(k+1) moves in as its CTAs retire, D2H(k) runs under trace(k+1).
+    // Cost: one host round trip (tens of microseconds) of idle GPU per sub-slab.
     for (size_t k = 0; k < nsub; ++k) {
         enqueue_trace(k);
-        if (k >= 1) finish(k - 1);
+        finish(k);
     }
-    if (nsub) finish(nsub - 1);
     FB_CUDA(cudaEventRecord(M->ev[5], s1));
     FB_CUDA(cudaEventRecord(M->ev[2], s0));
     unsigned long long tested = 0;

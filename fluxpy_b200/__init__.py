@@ -8,3 +8,4 @@ Python here is host glue over the C ABI of ``libfluxb200.so``
 from . import config  # noqa: F401
 from .form_factors import get_form_factor_matrix  # noqa: F401
 from .shape import CudaTrimeshShapeModel, TrimeshShapeModel, trimesh_shape_models  # noqa: F401
+from .device_csr import DeviceCsrSlab, get_form_factor_matrix_device  # noqa: F401

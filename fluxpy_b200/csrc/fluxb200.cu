@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "lbvh.cuh"
 #include "prims.cuh"
+#include "spmv.cuh"
 #include "trace.cuh"
 
 
@@ -50,6 +51,7 @@ struct fluxb200_mesh {
     DevBuf sbits[kSlots], scounts[kSlots], scounts64[kSlots], sindptr[kSlots], stage_data[kSlots], stage_idx[kSlots];
     HostBuf h_nnz, h_counts;
     int64_t dev_capacity_hint = 0;
+    int out_index_width = 0; // index width of the library-owned device CSR (0: none)
     int sub_rows_opt = 512;
     size_t m = 0, n = 0;
     int nwords = 0;
@@ -60,6 +62,17 @@ struct fluxb200_mesh {
     int trace_mode = 0;
 
     size_t esize() const { return dtype == FLUXB200_F64 ? 8 : 4; }
+};
+
+struct fluxb200_csr {
+    int device = 0;
+    int dtype = FLUXB200_F32;
+    int index_width = 4;
+    int64_t m = 0, n = 0, nnz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {};
+    DevBuf indptr, indices, data, scratch;
+    float last_ms = 0.f;
 };
 
 namespace {
@@ -478,6 +491,7 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_fill, M->ev[0], M->ev[1]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_d2h, M->ev[1], M->ev[2]));
     M->stats.kernel_launches += launches;
+    M->out_index_width = destination == 2 ? index_width : 0;
 }
 
 // ---- streaming assembly: row sub-slabs pipelined over two streams ------------------
@@ -649,7 +663,9 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
             for (size_t r = 0; r < m; ++r) ip[r + 1] = (run += h_counts[r]);
         }
     }
+    M->out_index_width = 0;
     if (destination == 2) { // device indptr for downstream device consumers
+        M->out_index_width = index_width;
         M->indptr.reserve(sizeof(int64_t) * (m + 1));
         std::vector<int64_t> ip(m + 1, 0);
         for (size_t r = 0; r < m; ++r) ip[r + 1] = ip[r] + h_counts[r];
@@ -921,6 +937,118 @@ int fluxb200_ff_device_csr(fluxb200_mesh *M, void **indptr, void **indices, void
         if (indices) *indices = M->out_indices.p;
         if (data) *data = M->out_data.p;
         if (nnz) *nnz = M->nnz;
+    });
+}
+
+// ---- device-resident CSR slab: detach, products, download -----
+int fluxb200_ff_detach_csr(fluxb200_mesh *M, fluxb200_csr **out) {
+    return guarded([&] {
+        FB_REQUIRE(M && out, "NULL argument");
+        FB_REQUIRE(M->have_count && M->out_index_width != 0, "no device-resident matrix on this handle "
+                   "(run fluxb200_ff_assemble / fluxb200_ff_fill with destination 2 first)");
+        DeviceGuard guard(M->device);
+        fluxb200_csr *C = new fluxb200_csr();
+        C->device = M->device;
+        C->dtype = M->dtype;
+        C->index_width = M->out_index_width;
+        C->m = (int64_t)M->m;
+        C->n = (int64_t)M->n;
+        C->nnz = M->nnz;
+        FB_CUDA(cudaStreamCreateWithFlags(&C->stream, cudaStreamNonBlocking));
+        for (auto &e : C->ev) FB_CUDA(cudaEventCreate(&e));
+        std::swap(C->indptr, M->indptr);
+        std::swap(C->indices, M->out_indices);
+        std::swap(C->data, M->out_data);
+        M->have_count = false;
+        M->out_index_width = 0;
+        M->dev_capacity_hint = 0;
+        *out = C;
+    });
+}
+
+int fluxb200_csr_destroy(fluxb200_csr *C) {
+    if (!C) return 0;
+    return guarded([&] {
+        DeviceGuard guard(C->device);
+        if (C->stream) cudaStreamSynchronize(C->stream);
+        C->indptr.release();
+        C->indices.release();
+        C->data.release();
+        C->scratch.release();
+        for (auto &e : C->ev)
+            if (e) cudaEventDestroy(e);
+        if (C->stream) cudaStreamDestroy(C->stream);
+        delete C;
+    });
+}
+
+int fluxb200_csr_info(fluxb200_csr *C, int64_t *m, int64_t *n, int64_t *nnz, int *dtype_code, int *index_width,
+                      float *last_ms) {
+    return guarded([&] {
+        FB_REQUIRE(C, "csr is NULL");
+        if (m) *m = C->m;
+        if (n) *n = C->n;
+        if (nnz) *nnz = C->nnz;
+        if (dtype_code) *dtype_code = C->dtype;
+        if (index_width) *index_width = C->index_width;
+        if (last_ms) *last_ms = C->last_ms;
+    });
+}
+
+int fluxb200_csr_to_host(fluxb200_csr *C, void *indptr, void *indices, void *data) {
+    return guarded([&] {
+        FB_REQUIRE(C, "csr is NULL");
+        DeviceGuard guard(C->device);
+        const size_t es = C->dtype == FLUXB200_F64 ? 8 : 4;
+        if (indptr) { // int64 on the device; narrowed on the host side if asked
+            std::vector<int64_t> ip((size_t)C->m + 1);
+            FB_CUDA(cudaMemcpyAsync(ip.data(), C->indptr.p, sizeof(int64_t) * ip.size(), cudaMemcpyDeviceToHost, C->stream));
+            FB_CUDA(cudaStreamSynchronize(C->stream));
+            if (C->index_width == 4)
+                for (size_t k = 0; k < ip.size(); ++k) reinterpret_cast<int32_t *>(indptr)[k] = (int32_t)ip[k];
+            else
+                memcpy(indptr, ip.data(), sizeof(int64_t) * ip.size());
+        }
+        if (indices && C->nnz)
+            FB_CUDA(cudaMemcpyAsync(indices, C->indices.p, (size_t)C->index_width * (size_t)C->nnz, cudaMemcpyDeviceToHost, C->stream));
+        if (data && C->nnz)
+            FB_CUDA(cudaMemcpyAsync(data, C->data.p, es * (size_t)C->nnz, cudaMemcpyDeviceToHost, C->stream));
+        FB_CUDA(cudaStreamSynchronize(C->stream));
+    });
+}
+
+int fluxb200_csr_jacobi_step(fluxb200_csr *C, const double *E_dev, const double *rho_dev, double rho_scalar,
+                             const double *x_dev, double *y_dev, double *diffmax_host, int64_t row_offset) {
+    return guarded([&] {
+        FB_REQUIRE(C && x_dev && y_dev, "NULL argument");
+        DeviceGuard guard(C->device);
+        if (diffmax_host) FB_REQUIRE(row_offset >= 0 && row_offset + C->m <= C->n, "row_offset outside the iterate");
+        C->scratch.reserve(sizeof(unsigned long long));
+        unsigned long long *dm = diffmax_host ? C->scratch.as<unsigned long long>() : nullptr;
+        if (dm) FB_CUDA(cudaMemsetAsync(dm, 0, sizeof(unsigned long long), C->stream));
+        FB_CUDA(cudaEventRecord(C->ev[0], C->stream));
+        if (C->m) {
+            const unsigned grid = (unsigned)C->m;
+#define FB_SPMV(TT, II)                                                                                   \
+    csr_jacobi_kernel<TT, II><<<grid, kSpmvThreads, 0, C->stream>>>(                                      \
+        C->indptr.as<int64_t>(), C->indices.as<II>(), C->data.as<TT>(), (int)C->m, E_dev, rho_dev, rho_scalar, \
+        x_dev, y_dev, dm, row_offset)
+            if (C->dtype == FLUXB200_F64) {
+                if (C->index_width == 4) FB_SPMV(double, int32_t);
+                else FB_SPMV(double, int64_t);
+            } else {
+                if (C->index_width == 4) FB_SPMV(float, int32_t);
+                else FB_SPMV(float, int64_t);
+            }
+#undef FB_SPMV
+            FB_CUDA(cudaGetLastError());
+        }
+        FB_CUDA(cudaEventRecord(C->ev[1], C->stream));
+        unsigned long long bits = 0;
+        if (dm) FB_CUDA(cudaMemcpyAsync(&bits, dm, sizeof(bits), cudaMemcpyDeviceToHost, C->stream));
+        FB_CUDA(cudaStreamSynchronize(C->stream));
+        FB_CUDA(cudaEventElapsedTime(&C->last_ms, C->ev[0], C->ev[1]));
+        if (diffmax_host) memcpy(diffmax_host, &bits, sizeof(double));
     });
 }
 

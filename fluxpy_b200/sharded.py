@@ -48,10 +48,11 @@ def exchange_row_counts(local_counts, starts, group=None, device=None):
 class SlabResult:
     """What one rank holds after a sharded assembly."""
 
-    def __init__(self, row_start, row_stop, global_indptr, local_csr, stats):
+    def __init__(self, row_start, row_stop, global_indptr, local_csr, stats, device_csr=None):
         self.row_start, self.row_stop = int(row_start), int(row_stop)
         self.global_indptr = global_indptr
         self.local_csr = local_csr       # scipy CSR of my rows (None in device-resident mode)
+        self.device_csr = device_csr     # DeviceCsrSlab of my rows (device-resident mode)
         self.stats = stats
 
     @property
@@ -80,11 +81,16 @@ def get_form_factor_matrix_sharded(shape_model, I=None, J=None, eps=None, group=
         local = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n), copy=False)
         local.has_sorted_indices = True
     else:
+        import ctypes
+        from .device_csr import DeviceCsrSlab
         m, n, counts, st = shape_model._ff_assemble_device(I[lo:hi], J, eps, 4, want_row_counts=True)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fluxb200_ff_detach_csr(shape_model._handle, ctypes.byref(h)))
+        dcsr = DeviceCsrSlab(h, shape_model.device, lo, len(I))
     dev = None
     if dist.get_backend(group) == 'nccl':
         import torch
         dev = torch.device('cuda', shape_model.device)
     # the one collective of the path: per-row counts -> global indptr on every rank
     indptr = exchange_row_counts(counts, starts, group, dev)
-    return SlabResult(lo, hi, indptr, local, st.as_dict())
+    return SlabResult(lo, hi, indptr, local, st.as_dict(), None if to_host else dcsr)

@@ -34,13 +34,14 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 2
+#define FLUXB200_ABI_VERSION 3
 
 #define FLUXB200_OK 0
 #define FLUXB200_ERROR 1
 #define FLUXB200_OVERFLOW 2 /* fluxb200_ff_assemble: `capacity` too small, see stats.nnz */
 
 typedef struct fluxb200_mesh fluxb200_mesh; /* cf. struct cgal_aabb, aabb_wrapper.h:6 */
+typedef struct fluxb200_csr fluxb200_csr;   /* a CSR slab resident in device memory */
 
 /* Counters and device timings of the last assembly on a handle. */
 typedef struct fluxb200_ff_stats {
@@ -139,6 +140,25 @@ int fluxb200_host_free(void *ptr);
 /* Device pointers of the library-owned CSR of the last destination==2 fill / assemble. */
 int fluxb200_ff_device_csr(fluxb200_mesh *mesh, void **indptr, void **indices, void **data,
                            int64_t *nnz);
+
+/* ---- device-resident slab: products for the radiosity iteration (next row N2) -- */
+
+/* Take ownership of the library-owned device CSR of the last destination==2
+ * assembly (rows = the I of that call).  The mesh handle can assemble again. */
+int fluxb200_ff_detach_csr(fluxb200_mesh *mesh, fluxb200_csr **out);
+int fluxb200_csr_destroy(fluxb200_csr *csr);
+int fluxb200_csr_info(fluxb200_csr *csr, int64_t *m, int64_t *n, int64_t *nnz, int *dtype_code,
+                      int *index_width, float *last_ms);
+/* Download (what scipy.sparse.save_npz would store); indptr/indices in the slab's index width. */
+int fluxb200_csr_to_host(fluxb200_csr *csr, void *indptr, void *indices, void *data);
+/* y = E + FF @ (rho * x) on the slab: one step of _solve_radiosity_jacobi_right
+ * (src/flux/solve.py:36-45); with E = NULL, rho = 1 it is the plain product FF @ x
+ * of src/flux/model.py:17.  All vectors are DEVICE pointers to float64: E[m] or
+ * NULL, rho[n] or NULL (then rho_scalar is used), x[n], y[m].  When diffmax_host
+ * is not NULL it receives max_r |y[r] - x[row_offset + r]| (solve.py:41). */
+int fluxb200_csr_jacobi_step(fluxb200_csr *csr, const double *E_dev, const double *rho_dev,
+                             double rho_scalar, const double *x_dev, double *y_dev,
+                             double *diffmax_host, int64_t row_offset);
 
 /* ---- TrimeshShapeModel hooks (src/flux/shape.py:129-188, 349-421) ---------- */
 

@@ -187,3 +187,37 @@ def test_full_50k_matrix_properties(mods):
     FO = mods['oracle'].get_form_factor_matrix(om, rows)
     assert same_csr(mods['ff'].get_form_factor_matrix(sm, rows), FO)
     assert np.array_equal(np.diff(FO.indptr), counts[rows])
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_device_resident_radiosity_and_steady_state(mods, dtype):
+    """Next row N2: Jacobi radiosity + steady-state temperature on the
+    device-resident matrix == the reference's own T (golden, model.py:8-24)
+    to 1e-6 relative L2, same iteration counts as the CPU restatement."""
+    from fluxpy_b200 import solve, get_form_factor_matrix_device
+    from oracle import radiosity
+    from tests import helpers
+    tag = np.dtype(dtype).name
+    g = helpers.load('crater_n24_s1')
+    V, F = mods['meshes'].gaussian_crater(24, 1, dtype=dtype)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    FFd = get_form_factor_matrix_device(sm)
+    FFh = mods['ff'].get_form_factor_matrix(sm)
+    D = FFd.to_scipy()
+    assert same_csr(D, FFh) and FFd.nnz == FFh.nnz and FFd.shape == FFh.shape
+    x = np.random.default_rng(0).normal(size=FFh.shape[1])
+    assert np.allclose(FFd@x, FFh@x, rtol=1e-12, atol=1e-14)
+    E = sm.get_direct_irradiance(1365.0, g[f'Dsun_{tag}']).astype(np.float64)
+    for rho in (0.12, np.linspace(0.05, 0.3, FFh.shape[0])):
+        B, nit = solve.solve_radiosity(FFd, E, rho)
+        Bref, nref = radiosity.solve_radiosity_jacobi_right(FFh, E, rho)
+        assert nit == nref and np.allclose(B, Bref, rtol=1e-13, atol=1e-10)
+        Bl, _ = solve.solve_radiosity(FFd, E, rho, albedo_placement='left')
+        assert np.allclose(Bl[E > 0], B[E > 0], rtol=0.5) and np.isfinite(Bl).all()
+    T = solve.compute_steady_state_temp(FFd, E, 0.12, 0.95)
+    Tref = g[f'T_{tag}']
+    assert np.linalg.norm(T - Tref) <= 1e-6*np.linalg.norm(Tref)
+    with pytest.raises(RuntimeError):            # rho = 5: diverges, the reference would hang (P13)
+        solve.solve_radiosity(FFd, E, 5.0, maxiter=200)
+    # the mesh handle is free for the next assembly after the detach
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm), FFh)

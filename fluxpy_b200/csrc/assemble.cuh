@@ -212,10 +212,12 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
 }
 
 // ---------------------------------------------------------------------------
-// K6: CSR fill.  One CTA per (row, part); columns are visited in ORIGINAL J
-// order so every row comes out with ascending column positions
-// (form_factors.py:52, 69).  The row's visibility words (sorted-column order)
-// are staged in shared memory and looked up through rank_of_pos.
+// K6: CSR fill.  One CTA per row; columns are visited in ORIGINAL J order so
+// every row comes out with ascending column positions (form_factors.py:52,
+// 69).  The row's visibility words (sorted-column order) are staged in shared
+// memory and looked up through rank_of_pos.  Each warp owns a contiguous
+// segment of the columns: one counting pass, one block-wide prefix over the 8
+// warp totals (the only barrier), one writing pass.
 // ---------------------------------------------------------------------------
 constexpr int kFillThreads = 256;
 
@@ -238,7 +240,6 @@ template <class T>
 __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A) {
     extern __shared__ uint32_t bits_s[];
     __shared__ uint32_t warp_tot[kFillThreads / 32];
-    __shared__ uint32_t running_s;
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row_begin = A.out_base + A.indptr[r];
@@ -246,45 +247,72 @@ __global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A)
     const uint32_t *gbits = A.bits + (size_t)r * A.nwords;
     if (A.bits_in_smem) {
         for (int k = threadIdx.x; k < A.nwords; k += kFillThreads) bits_s[k] = gbits[k];
+        __syncthreads();
     }
-    if (threadIdx.x == 0) running_s = 0;
-    __syncthreads();
     const uint32_t *bits = A.bits_in_smem ? bits_s : gbits;
+    // every warp owns one contiguous segment of the ORIGINAL column order (multiple of 32 columns)
+    const int groups = (A.n + 31) / 32;
+    const int gper = (groups + kFillThreads / 32 - 1) / (kFillThreads / 32);
+    const int q_begin = min(A.n, warp * gper * 32), q_end = min(A.n, (warp + 1) * gper * 32);
+    // pass 1: entries in my segment (four independent lookups in flight per lane)
+    constexpr int U = 4;
+    uint32_t cnt = 0;
+    for (int q0 = q_begin; q0 < q_end; q0 += 32 * U) {
+        int sidx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * 32 + lane;
+            sidx[u] = q < q_end ? A.rank_of_pos[q] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool set = sidx[u] >= 0 && ((bits[sidx[u] >> 5] >> (sidx[u] & 31)) & 1u);
+            cnt += __popc(__ballot_sync(0xffffffffu, set));
+        }
+    }
+    if (lane == 0) warp_tot[warp] = cnt;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    // pass 2: values (fp64, rounded once) and column positions, in ascending order
     const int i = A.rows[r];
     const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
-    for (int q0 = 0; q0 < A.n; q0 += kFillThreads) {
-        const int q = q0 + threadIdx.x;
-        bool set = false;
-        if (q < A.n) {
-            const int s = A.rank_of_pos[q];
-            set = (bits[s >> 5] >> (s & 31)) & 1u;
+    for (int q0 = q_begin; q0 < q_end; q0 += 32 * U) {
+        int sidx[U], jj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * 32 + lane;
+            sidx[u] = q < q_end ? A.rank_of_pos[q] : -1;
+            jj[u] = q < q_end ? A.cols[q] : 0;
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, set);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        uint32_t off = running_s;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        if (set) {
-            const int j = A.cols[q];
-            const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
-            double dx, dy, dz;
-            double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
-            if (j == i) num = 0.0;
-            const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
-            const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                 // :62
-            const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj.w), sden); // :63-64
-            const int64_t dst = row_begin + off + __popc(bal & ((1u << lane) - 1u));
-            A.data[dst] = (T)v;
-            if (A.index_width == 4) reinterpret_cast<int32_t *>(A.indices)[dst] = q;
-            else reinterpret_cast<int64_t *>(A.indices)[dst] = q;
+        bool set[U];
+        Real4<T> Pj[U], Nj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            set[u] = sidx[u] >= 0 && ((bits[sidx[u] >> 5] >> (sidx[u] & 31)) & 1u);
+            if (set[u]) {
+                Pj[u] = load_real4<T>(A.faceP + jj[u]);
+                Nj[u] = load_real4<T>(A.faceN + jj[u]);
+            }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < kFillThreads / 32; ++w) t += warp_tot[w];
-            running_s += t;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, set[u]);
+            if (set[u]) {
+                double dx, dy, dz;
+                double num = numerator<T>(Pi, Ni, Pj[u], Nj[u], dx, dy, dz);
+                if (jj[u] == i) num = 0.0;
+                const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
+                const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                 // :62
+                const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj[u].w), sden); // :63-64
+                const int64_t dst = row_begin + off + __popc(bal & ((1u << lane) - 1u));
+                A.data[dst] = (T)v;
+                const int q = q0 + u * 32 + lane;
+                if (A.index_width == 4) reinterpret_cast<int32_t *>(A.indices)[dst] = q;
+                else reinterpret_cast<int64_t *>(A.indices)[dst] = q;
+            }
+            off += __popc(bal);
         }
-        __syncthreads();
     }
 }
 

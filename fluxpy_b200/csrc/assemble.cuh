@@ -55,6 +55,8 @@ template <> __device__ __forceinline__ Real4<double> load_real4<double>(const Re
 template <class T> struct TraceArgs {
     const Real4<T> *faceP, *faceN;  // per face, original order
     const int *rows;                // m face ids (I)
+    const int *face_leaf;           // leaf position of every face
+    const int *node_up, *leaf_up;   // (parent node << 1 | slot) of every internal node / leaf, -1 = none
     const Real4<T> *colP, *colN;    // n columns gathered in leaf (Morton) order
     const int *col_face, *col_leaf; // face id / leaf position of sorted column s
     int m, n, nwords;               // nwords = ceil(n/32)
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
     extern __shared__ float4 smem_top[];
     __shared__ uint32_t words_s[kTraceWarps][32];
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
+    __shared__ float4 path_s[kTop ? 1 : kTraceWarps][kTop ? 1 : 3 * kStackDepth];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     if (kTop) {
         for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
@@ -106,6 +109,28 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         const int i = A.rows[r];
         const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
         const int s0 = c * kChunkCols;
+        // Every ray of this unit starts on triangle i, so every traversal would walk
+        // root -> leaf(i) and test, level by level, the subtree hanging off that path.
+        // List those child records once (the source leaf's own record first, then the
+        // sibling at every level up to the root): the batches below test them in a
+        // uniform loop with broadcast shared-memory loads instead of descending from the root.
+        int npath = 0;
+        if (!kTop && A.ninternal > 0) {
+            int code = A.leaf_up[A.face_leaf[i]];
+            bool own = true; // first entry: the leaf's own record, then siblings
+            while (code >= 0) {
+                const int p = code >> 1, slot = code & 1;
+                if (own) {
+                    if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(A.nodes + 6 * (size_t)p + 3 * slot + lane);
+                    ++npath;
+                    own = false;
+                }
+                if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(A.nodes + 6 * (size_t)p + 3 * (1 - slot) + lane);
+                ++npath;
+                code = A.node_up[p];
+            }
+            __syncwarp();
+        }
         // ---- phase 1: cull -----------------------------------------------------
         uint32_t myword = 0;
 #pragma unroll 4
@@ -175,6 +200,26 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 if (blocked) active = false;
             };
             // (the tree depth was checked against kStackDepth when it was built)
+            if (!kTop) {
+                // phase A: the records along the source path, same for all lanes
+                for (int e = 0; e < npath; ++e) {
+                    const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
+                    if (active && child_hit(ray, rb, a, b, cc, tmax)) {
+                        const int ref = __float_as_int(a.w);
+                        if (ref < 0) {
+                            if (~ref != tleaf) leaf_s[nl++][tid] = ~ref;
+                        } else {
+                            stack[sp++] = ref;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
+                }
+                // phase B: whatever was hit (normally only the subtree holding the target)
+                if (active) {
+                    if (sp > 0) node = stack[--sp];
+                    else active = false;
+                }
+            }
             while (__any_sync(0xffffffffu, active)) {
                 if (active) {
                     float4 q[6];

@@ -31,7 +31,7 @@ struct fluxb200_mesh {
     DevBuf V, F, V32, faceP, faceN; // geometry
     // LBVH
     DevBuf keys, vals, left, right, parent, first, last, box, slab, flags, pre, flag_by_pre, top_before,
-        scene, scalars, nodes, tri, face_leaf;
+        scene, scalars, nodes, tri, face_leaf, node_up, leaf_up;
     RadixSorter sorter;
     int nnodes = 0, ninternal = 0, ntop = 0, max_depth = 0;
     int top_nodes_opt = 0;   // measured: L1 already serves the top of the tree (profiles/)
@@ -159,6 +159,9 @@ void bvh_build(fluxb200_mesh *M) {
     M->nodes.reserve(sizeof(float4) * 6 * std::max(n - 1, 1));
     M->tri.reserve(sizeof(float4) * 3 * n);
     M->face_leaf.reserve(sizeof(int) * n);
+    M->node_up.reserve(sizeof(int) * n);
+    M->leaf_up.reserve(sizeof(int) * n);
+    FB_CUDA(cudaMemsetAsync(M->leaf_up.p, 0xff, sizeof(int) * n, st)); // single-face mesh: no parent
 
     FB_CUDA(cudaEventRecord(M->ev[0], st));
     const unsigned scene_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
@@ -210,7 +213,8 @@ void bvh_build(fluxb200_mesh *M) {
                                                            M->pre.as<int>(), M->top_before.as<int>(),
                                                            M->flag_by_pre.as<int>(), scal + 0,
                                                            M->box.as<float>(), M->slab.as<unsigned>(),
-                                                           M->scene.as<unsigned>(), M->nodes.as<float4>());
+                                                           M->scene.as<unsigned>(), M->nodes.as<float4>(),
+                                                           M->node_up.as<int>(), M->leaf_up.as<int>());
     }
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaEventRecord(M->ev[1], st));
@@ -334,6 +338,9 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.faceP = M->faceP.as<Real4<T>>();
     A.faceN = M->faceN.as<Real4<T>>();
     A.rows = M->rows.as<int>() + row0;
+    A.face_leaf = M->face_leaf.as<int>();
+    A.node_up = M->node_up.as<int>();
+    A.leaf_up = M->leaf_up.as<int>();
     A.colP = M->colP.as<Real4<T>>();
     A.colN = M->colN.as<Real4<T>>();
     A.col_face = M->col_face.as<int>();
@@ -798,7 +805,7 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
         if (M->stream) cudaStreamSynchronize(M->stream);
         DevBuf *bufs[] = {&M->V, &M->F, &M->V32, &M->faceP, &M->faceN, &M->keys, &M->vals, &M->left, &M->right,
                           &M->parent, &M->first, &M->last, &M->box, &M->slab, &M->flags, &M->pre, &M->flag_by_pre,
-                          &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->rows,
+                          &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->rows,
                           &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
                           &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};

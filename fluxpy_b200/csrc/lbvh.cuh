@@ -328,7 +328,8 @@ __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *_
                                const int *__restrict__ pre, const int *__restrict__ top_before,
                                const int *__restrict__ flag_by_pre, const int *__restrict__ ntop_p,
                                const float *__restrict__ box, const unsigned *__restrict__ slab,
-                               const unsigned *__restrict__ scene, float4 *__restrict__ nodes) {
+                               const unsigned *__restrict__ scene, float4 *__restrict__ nodes,
+                               int *__restrict__ node_up, int *__restrict__ leaf_up) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n - 1) return;
     const int ntop = *ntop_p;
@@ -338,11 +339,16 @@ __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *_
     };
     const float pad = 8.0e-6f * ord_flt(scene[6]) + 1e-30f;
     const int me = final_id(x);
+    if (x == 0) node_up[me] = -1; // root
     const int ch[2] = {left[x], right[x]};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const int y = ch[c];
         const int ref = (y >= n - 1) ? ~(y - (n - 1)) : final_id(y);
+        // "up" link of the child: (parent node << 1) | slot -- lets a warp list the
+        // siblings along the root -> source-triangle path (see trace_kernel)
+        if (y >= n - 1) leaf_up[y - (n - 1)] = (me << 1) | c;
+        else node_up[ref] = (me << 1) | c;
         const float *b = box + 9 * (size_t)y;
         const unsigned umin = slab[2 * (size_t)y], umax = slab[2 * (size_t)y + 1];
         float smin = -INFINITY, smax = INFINITY;

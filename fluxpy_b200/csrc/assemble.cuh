@@ -57,6 +57,7 @@ template <class T> struct TraceArgs {
     const int *rows;                // m face ids (I)
     const int *face_leaf;           // leaf position of every face
     const int *node_up, *leaf_up;   // (parent node << 1 | slot) of every internal node / leaf, -1 = none
+    const int2 *node_range;         // first / last leaf position under every internal node
     const Real4<T> *colP, *colN;    // n columns gathered in leaf (Morton) order
     const int *col_face, *col_leaf; // face id / leaf position of sorted column s
     int m, n, nwords;               // nwords = ceil(n/32)
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
     __shared__ uint32_t words_s[kTraceWarps][32];
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
     __shared__ float4 path_s[kTop ? 1 : kTraceWarps][kTop ? 1 : 3 * kStackDepth];
+    __shared__ int2 range_s[kTop ? 1 : kTraceWarps][kTop ? 1 : kStackDepth];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     if (kTop) {
         for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
@@ -116,16 +118,23 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         // uniform loop with broadcast shared-memory loads instead of descending from the root.
         int npath = 0;
         if (!kTop && A.ninternal > 0) {
-            int code = A.leaf_up[A.face_leaf[i]];
+            const int ileaf = A.face_leaf[i];
+            int code = A.leaf_up[ileaf];
             bool own = true; // first entry: the leaf's own record, then siblings
             while (code >= 0) {
                 const int p = code >> 1, slot = code & 1;
                 if (own) {
                     if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(A.nodes + 6 * (size_t)p + 3 * slot + lane);
+                    if (lane == 3) range_s[warp][npath] = make_int2(ileaf, ileaf);
                     ++npath;
                     own = false;
                 }
-                if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(A.nodes + 6 * (size_t)p + 3 * (1 - slot) + lane);
+                const float4 *rec = A.nodes + 6 * (size_t)p + 3 * (1 - slot);
+                if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(rec + lane);
+                if (lane == 3) {
+                    const int ref = __float_as_int(__ldg(rec).w);
+                    range_s[warp][npath] = ref < 0 ? make_int2(~ref, ~ref) : A.node_range[ref];
+                }
                 ++npath;
                 code = A.node_up[p];
             }
@@ -201,20 +210,43 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             };
             // (the tree depth was checked against kStackDepth when it was built)
             if (!kTop) {
-                // phase A: the records along the source path, same for all lanes
+                // phase A: the records along the source path, same for all lanes.  The one
+                // sibling subtree that holds the target (X) is not tested: its inside is
+                // covered by phase B.
+                int xref = ~tleaf;
                 for (int e = 0; e < npath; ++e) {
                     const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
-                    if (active && child_hit(ray, rb, a, b, cc, tmax)) {
-                        const int ref = __float_as_int(a.w);
-                        if (ref < 0) {
-                            if (~ref != tleaf) leaf_s[nl++][tid] = ~ref;
-                        } else {
-                            stack[sp++] = ref;
+                    const int2 rg = range_s[warp][e];
+                    const int ref = __float_as_int(a.w);
+                    if (tleaf >= rg.x && tleaf <= rg.y) {
+                        xref = ref;
+                    } else if (active && child_hit(ray, rb, a, b, cc, tmax)) {
+                        if (ref < 0) leaf_s[nl++][tid] = ~ref;
+                        else if (sp < kStackDepth) stack[sp++] = ref;
+                        else *A.error_flag = 1;
+                    }
+                    if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
+                }
+                // phase B: from the target leaf up to X, the sibling at every level
+                // (one record per level instead of a two-child node per level from the root)
+                int cur = ~tleaf, code = tleaf >= 0 ? A.leaf_up[tleaf] : -1;
+                while (__any_sync(0xffffffffu, active && cur != xref && code >= 0)) {
+                    if (active && cur != xref && code >= 0) {
+                        const int p = code >> 1, slot = code & 1;
+                        const float4 *rec = A.nodes + 6 * (size_t)p + 3 * (1 - slot);
+                        const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
+                        code = A.node_up[p];
+                        cur = p;
+                        if (child_hit(ray, rb, a, b, cc, tmax)) {
+                            const int ref = __float_as_int(a.w);
+                            if (ref < 0) leaf_s[nl++][tid] = ~ref;
+                            else if (sp < kStackDepth) stack[sp++] = ref;
+                            else *A.error_flag = 1;
                         }
                     }
                     if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
                 }
-                // phase B: whatever was hit (normally only the subtree holding the target)
+                // phase C: the subtrees that were actually hit, top-down
                 if (active) {
                     if (sp > 0) node = stack[--sp];
                     else active = false;

@@ -31,7 +31,7 @@ struct fluxb200_mesh {
     DevBuf V, F, V32, faceP, faceN; // geometry
     // LBVH
     DevBuf keys, vals, left, right, parent, first, last, box, slab, flags, pre, flag_by_pre, top_before,
-        scene, scalars, nodes, tri, face_leaf, node_up, leaf_up;
+        scene, scalars, nodes, tri, face_leaf, node_up, leaf_up, node_range;
     RadixSorter sorter;
     int nnodes = 0, ninternal = 0, ntop = 0, max_depth = 0;
     int top_nodes_opt = 0;   // measured: L1 already serves the top of the tree (profiles/)
@@ -161,6 +161,7 @@ void bvh_build(fluxb200_mesh *M) {
     M->face_leaf.reserve(sizeof(int) * n);
     M->node_up.reserve(sizeof(int) * n);
     M->leaf_up.reserve(sizeof(int) * n);
+    M->node_range.reserve(sizeof(int2) * n);
     FB_CUDA(cudaMemsetAsync(M->leaf_up.p, 0xff, sizeof(int) * n, st)); // single-face mesh: no parent
 
     FB_CUDA(cudaEventRecord(M->ev[0], st));
@@ -214,7 +215,9 @@ void bvh_build(fluxb200_mesh *M) {
                                                            M->flag_by_pre.as<int>(), scal + 0,
                                                            M->box.as<float>(), M->slab.as<unsigned>(),
                                                            M->scene.as<unsigned>(), M->nodes.as<float4>(),
-                                                           M->node_up.as<int>(), M->leaf_up.as<int>());
+                                                           M->node_up.as<int>(), M->leaf_up.as<int>(),
+                                                           M->first.as<int>(), M->last.as<int>(),
+                                                           M->node_range.as<int2>());
     }
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaEventRecord(M->ev[1], st));
@@ -341,6 +344,7 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.face_leaf = M->face_leaf.as<int>();
     A.node_up = M->node_up.as<int>();
     A.leaf_up = M->leaf_up.as<int>();
+    A.node_range = M->node_range.as<int2>();
     A.colP = M->colP.as<Real4<T>>();
     A.colN = M->colN.as<Real4<T>>();
     A.col_face = M->col_face.as<int>();
@@ -805,7 +809,7 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
         if (M->stream) cudaStreamSynchronize(M->stream);
         DevBuf *bufs[] = {&M->V, &M->F, &M->V32, &M->faceP, &M->faceN, &M->keys, &M->vals, &M->left, &M->right,
                           &M->parent, &M->first, &M->last, &M->box, &M->slab, &M->flags, &M->pre, &M->flag_by_pre,
-                          &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->rows,
+                          &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->node_range, &M->rows,
                           &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
                           &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};

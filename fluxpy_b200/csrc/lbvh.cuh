@@ -329,7 +329,9 @@ __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *_
                                const int *__restrict__ flag_by_pre, const int *__restrict__ ntop_p,
                                const float *__restrict__ box, const unsigned *__restrict__ slab,
                                const unsigned *__restrict__ scene, float4 *__restrict__ nodes,
-                               int *__restrict__ node_up, int *__restrict__ leaf_up) {
+                               int *__restrict__ node_up, int *__restrict__ leaf_up,
+                               const int *__restrict__ first, const int *__restrict__ last,
+                               int2 *__restrict__ node_range) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n - 1) return;
     const int ntop = *ntop_p;
@@ -340,6 +342,7 @@ __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *_
     const float pad = 8.0e-6f * ord_flt(scene[6]) + 1e-30f;
     const int me = final_id(x);
     if (x == 0) node_up[me] = -1; // root
+    node_range[me] = make_int2(first[x], last[x]); // leaf positions covered by the node
     const int ch[2] = {left[x], right[x]};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {

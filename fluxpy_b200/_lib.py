@@ -196,11 +196,11 @@ class PinnedArena:
         for b in self.free:
             if b.nbytes >= nbytes and (best is None or b.nbytes < best.nbytes):
                 best = b
-        if best is not None and best.nbytes <= 2*nbytes + (1 << 20):
+        if best is not None and best.nbytes <= 8*nbytes + (1 << 20):
             self.free.remove(best)
             return best
         p = ctypes.c_void_p()
-        want = nbytes + nbytes//16 + 4096
+        want = nbytes + nbytes//8 + 4096          # page-locking is slow: leave room to be reused
         check(lib().fluxb200_host_alloc(want, ctypes.byref(p)))
         return _Block(p.value, want)
 

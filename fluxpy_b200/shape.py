@@ -262,7 +262,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
-    #: largest nnz / (m*n) seen so far (slowly forgotten): sizes the streaming
+    #: largest nnz / (m*n) seen so far: sizes the streaming
     #: output buffers, with 20 % headroom, so that a retry is the exception
     _fill_ratio = 0.55
     overflow_retries = 0
@@ -301,7 +301,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             break
         nnz = int(st.nnz)
         if m*n:
-            type(self)._fill_ratio = max(0.02, nnz/(m*n), 0.98*self._fill_ratio)
+            type(self)._fill_ratio = max(0.02, nnz/(m*n), self._fill_ratio)
         data, indices, indptr = _lib.arena.arrays(
             block, [(0, nnz, self.dtype), (off_idx, nnz, idt), (off_ptr, m + 1, idt)])
         return m, n, indptr, indices, data, counts, st

@@ -63,7 +63,9 @@ def workload(args):
 def slab_rows(step, rank, world, rows, nf):
     """Rows of slab number step*world + rank (slabs tile the matrix top to bottom, wrapping)."""
     nslabs = max(1, nf//rows)          # equal slabs only (the remainder rows are not benched)
-    s = (step*world + rank) % nslabs
+    # stride 7 (coprime to the 48 slabs of the 200k mesh): every run samples rim, wall and floor
+    # rows alike, whatever the number of ranks -- slab cost varies by +-15 % across the crater
+    s = ((step*world + rank)*7) % nslabs
     lo = s*rows
     return np.arange(lo, min(nf, lo + rows), dtype=np.int64)
 
@@ -118,6 +120,15 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
                 'samples': len(sm)}
+
+
+def measured_traffic():
+    """DRAM bytes of one trace-kernel launch from the committed ncu capture
+    (profiles/r01_trace_kernel_traffic.json), or None."""
+    p = os.path.join(ROOT, 'profiles', 'r01_trace_kernel_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
 
 
 def measured_peaks():
@@ -327,7 +338,8 @@ def main():
         roof = {
             'kernel': 'trace_kernel<float> (fused cull + occlusion traversal)',
             'bound': 'fp32', 'achieved': fl/trace_s/1e12, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-            'frac': fl/trace_s/1e12/fp32_peak, 'traffic': None, 'peak_source': 'SMs*128*2*sm_max_mhz',
+            'frac': fl/trace_s/1e12/fp32_peak, 'traffic': (measured_traffic() or {}).get('dram_bytes_per_launch'),
+            'traffic_note': (measured_traffic() or {}).get('note'), 'peak_source': 'SMs*128*2*sm_max_mhz',
             'alg_flop_per_launch': fl, 'launch_ms': 1e3*trace_s, 'launches_per_step': nl/steps,
             'hbm': {'bound': 'hbm', 'achieved': by/assemble_s/1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': by/assemble_s/1e9/hbm_peak, 'alg_bytes_per_step': by, 'peak_source': peak_src},

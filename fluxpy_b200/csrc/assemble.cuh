@@ -69,6 +69,7 @@ template <class T> struct TraceArgs {
     uint32_t *row_counts;           // m
     unsigned long long *tested;     // [0] rays traced, [1] work-unit counter of this launch
     int *error_flag;
+    float scale;                    // largest |coordinate| of the mesh (pads of the shaft filter)
 };
 
 constexpr int kLeafCap = 8; // deferred candidate triangles per lane
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
     __shared__ float4 path_s[kTop ? 1 : kTraceWarps][kTop ? 1 : 3 * kStackDepth];
     __shared__ int2 range_s[kTop ? 1 : kTraceWarps][kTop ? 1 : kStackDepth];
+    __shared__ unsigned char sel_s[kTop ? 1 : kTraceWarps][kTop ? 1 : kStackDepth];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     if (kTop) {
         for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
@@ -142,12 +144,18 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         }
         // ---- phase 1: cull -----------------------------------------------------
         uint32_t myword = 0;
+        float bl0 = INFINITY, bl1 = INFINITY, bl2 = INFINITY, bh0 = -INFINITY, bh1 = -INFINITY, bh2 = -INFINITY;
 #pragma unroll 4
         for (int k = 0; k < 32; ++k) {
             const int s = s0 + k * 32 + lane;
             bool keep = false;
             if (s < A.n) {
                 const Real4<T> Pj = load_real4<T>(A.colP + s), Nj = load_real4<T>(A.colN + s);
+                if (!kTop) { // bounding box of the chunk's target centroids (shaft filter below)
+                    bl0 = fminf(bl0, (float)Pj.x); bh0 = fmaxf(bh0, (float)Pj.x);
+                    bl1 = fminf(bl1, (float)Pj.y); bh1 = fmaxf(bh1, (float)Pj.y);
+                    bl2 = fminf(bl2, (float)Pj.z); bh2 = fmaxf(bh2, (float)Pj.z);
+                }
                 double dx, dy, dz;
                 double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
                 if (A.col_face[s] == i) num = 0.0; // row_data[i == J] = 0
@@ -155,6 +163,48 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             }
             const uint32_t w = __ballot_sync(0xffffffffu, keep);
             if (lane == k) myword = w;
+        }
+        // ---- shaft filter of the source-path list --------------------------------------
+        // Every ray of this unit lies in the convex hull of the source centroid and the
+        // chunk's target centroids.  A source-path record whose (padded) box or fitted slab is
+        // separated from that hull along x, y, z or its own slab direction cannot be hit by
+        // any of them: drop it for the whole unit.  Records holding targets always stay.
+        int nsel = 0;
+        if (!kTop && npath > 0) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                bl0 = fminf(bl0, __shfl_xor_sync(0xffffffffu, bl0, o)); bh0 = fmaxf(bh0, __shfl_xor_sync(0xffffffffu, bh0, o));
+                bl1 = fminf(bl1, __shfl_xor_sync(0xffffffffu, bl1, o)); bh1 = fmaxf(bh1, __shfl_xor_sync(0xffffffffu, bh1, o));
+                bl2 = fminf(bl2, __shfl_xor_sync(0xffffffffu, bl2, o)); bh2 = fmaxf(bh2, __shfl_xor_sync(0xffffffffu, bh2, o));
+            }
+            const int leaf_lo = A.col_leaf[s0], leaf_hi = A.col_leaf[min(A.n, s0 + kChunkCols) - 1];
+            const float px = (float)Pi.x, py = (float)Pi.y, pz = (float)Pi.z;
+            const float pad = 3e-5f * A.scale + 1e-4f * fmaxf(fmaxf(bh0 - bl0, bh1 - bl1), bh2 - bl2) + 2e-3f;
+            const float h0l = fminf(px, bl0) - pad, h0h = fmaxf(px, bh0) + pad;
+            const float h1l = fminf(py, bl1) - pad, h1h = fmaxf(py, bh1) + pad;
+            const float h2l = fminf(pz, bl2) - pad, h2h = fmaxf(pz, bh2) + pad;
+            for (int e0 = 0; e0 < npath; e0 += 32) {
+                const int e = e0 + lane;
+                bool keepr = false;
+                if (e < npath) {
+                    const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
+                    const int2 rg = range_s[warp][e];
+                    keepr = true;
+                    if (rg.y < leaf_lo || rg.x > leaf_hi) { // holds no target of this chunk
+                        if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keepr = false;
+                        // extent of the hull along the slab direction
+                        const float sp = cc.x * px + cc.y * py + cc.z * pz;
+                        const float lo_s = fminf(cc.x * bl0, cc.x * bh0) + fminf(cc.y * bl1, cc.y * bh1) + fminf(cc.z * bl2, cc.z * bh2);
+                        const float hi_s = fmaxf(cc.x * bl0, cc.x * bh0) + fmaxf(cc.y * bl1, cc.y * bh1) + fmaxf(cc.z * bl2, cc.z * bh2);
+                        const float spad = pad * (fabsf(cc.x) + fabsf(cc.y) + fabsf(cc.z));
+                        if (fminf(sp, lo_s) - spad > cc.w || fmaxf(sp, hi_s) + spad < b.w) keepr = false;
+                    }
+                }
+                const uint32_t kb = __ballot_sync(0xffffffffu, keepr);
+                if (keepr) sel_s[warp][nsel + __popc(kb & ((1u << lane) - 1u))] = (unsigned char)e;
+                nsel += __popc(kb);
+            }
+            __syncwarp();
         }
         // ---- phase 2: trace the survivors, 32 rays per batch ---------------------
         uint32_t incl = __popc(myword);
@@ -214,7 +264,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 // sibling subtree that holds the target (X) is not tested: its inside is
                 // covered by phase B.
                 int xref = ~tleaf;
-                for (int e = 0; e < npath; ++e) {
+                for (int ks = 0; ks < nsel; ++ks) {
+                    const int e = sel_s[warp][ks];
                     const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
                     const int2 rg = range_s[warp][e];
                     const int ref = __float_as_int(a.w);

@@ -362,6 +362,7 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.row_counts = row_counts;
     A.tested = M->tested.as<unsigned long long>();
     A.error_flag = M->scalars.as<int>() + 6;
+    A.scale = M->scene_h[6];
     A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         // sibling at every level up to the root): the batches below test them in a
         // uniform loop with broadcast shared-memory loads instead of descending from the root.
         int npath = 0;
+        int cref = -0x7fffffff; // common ancestor of the chunk's targets when usable (see below)
         if (!kTop && A.ninternal > 0) {
             const int ileaf = A.face_leaf[i];
             int code = A.leaf_up[ileaf];
@@ -141,6 +142,43 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 code = A.node_up[p];
             }
             __syncwarp();
+            // Target side, shared part: all targets of this chunk lie under their common
+            // ancestor C.  When one source-path record X holds the whole chunk, the siblings
+            // between X and C are the same for every ray of the unit: append them to the list
+            // (they go through the shaft filter and the uniform loop), and let the per-ray
+            // upward walk stop at C instead of X.
+            const int leaf_lo = A.col_leaf[s0], leaf_hi = A.col_leaf[min(A.n, s0 + kChunkCols) - 1];
+            int xe = -1;
+            for (int e = 0; e < npath; ++e)
+                if (range_s[warp][e].x <= leaf_lo && leaf_hi <= range_s[warp][e].y) xe = e;
+            if (xe >= 0 && leaf_lo != leaf_hi) {
+                const int xr = __float_as_int(path_s[warp][3 * xe].w);
+                int c = A.leaf_up[leaf_lo] >> 1;
+                while (!(A.node_range[c].x <= leaf_lo && leaf_hi <= A.node_range[c].y)) c = A.node_up[c] >> 1;
+                int cur = c, n2 = npath;
+                bool complete = true;
+                while (cur != xr) {
+                    const int up = A.node_up[cur];
+                    if (up < 0 || n2 >= kStackDepth) {
+                        complete = false;
+                        break;
+                    }
+                    const int pp = up >> 1, slot = up & 1;
+                    const float4 *rec = A.nodes + 6 * (size_t)pp + 3 * (1 - slot);
+                    if (lane < 3) path_s[warp][3 * n2 + lane] = __ldg(rec + lane);
+                    if (lane == 3) {
+                        const int ref = __float_as_int(__ldg(rec).w);
+                        range_s[warp][n2] = ref < 0 ? make_int2(~ref, ~ref) : A.node_range[ref];
+                    }
+                    ++n2;
+                    cur = pp;
+                }
+                if (complete) {
+                    npath = n2;
+                    cref = c;
+                }
+                __syncwarp();
+            }
         }
         // ---- phase 1: cull -----------------------------------------------------
         uint32_t myword = 0;
@@ -280,9 +318,10 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 }
                 // phase B: from the target leaf up to X, the sibling at every level
                 // (one record per level instead of a two-child node per level from the root)
+                const int stop = cref != -0x7fffffff ? cref : xref;
                 int cur = ~tleaf, code = tleaf >= 0 ? A.leaf_up[tleaf] : -1;
-                while (__any_sync(0xffffffffu, active && cur != xref && code >= 0)) {
-                    if (active && cur != xref && code >= 0) {
+                while (__any_sync(0xffffffffu, active && cur != stop && code >= 0)) {
+                    if (active && cur != stop && code >= 0) {
                         const int p = code >> 1, slot = code & 1;
                         const float4 *rec = A.nodes + 6 * (size_t)p + 3 * (1 - slot);
                         const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);

@@ -70,6 +70,7 @@ template <class T> struct TraceArgs {
     unsigned long long *tested;     // [0] rays traced, [1] work-unit counter of this launch
     int *error_flag;
     float scale;                    // largest |coordinate| of the mesh (pads of the shaft filter)
+    int shaft_filter;               // 0: test every record of the per-unit list (A/B check)
 };
 
 constexpr int kLeafCap = 8; // deferred candidate triangles per lane
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                     const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
                     const int2 rg = range_s[warp][e];
                     keepr = true;
-                    if (rg.y < leaf_lo || rg.x > leaf_hi) { // holds no target of this chunk
+                    if (A.shaft_filter && (rg.y < leaf_lo || rg.x > leaf_hi)) { // holds no target of this chunk
                         if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keepr = false;
                         // extent of the hull along the slab direction
                         const float sp = cc.x * px + cc.y * py + cc.z * pz;
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             Ray ray;
             int bit = 0, tleaf = -1, tface = 0;
             float tj = 0.f;
-            bool active = false, blocked = false;
+            bool active = false, blocked = false, overshoot = false;
             if (want < total) {
                 bit = __fns(wk, 0, (int)(want - before) + 1);
                 const int s = s0 + k * 32 + bit;
@@ -278,8 +279,17 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 if (setup_ray(Pi, Pj, ray)) { // else masked pair: "vis by default" (shape.py:392)
                     tleaf = A.col_leaf[s];
                     tface = A.col_face[s];
-                    if (target_hit_t(bvh, ray, tleaf, tj)) active = A.ninternal > 0;
-                    else blocked = true; // the ray misses its own target: closest hit is not j
+                    if (target_hit_t(bvh, ray, tleaf, tj)) {
+                        active = A.ninternal > 0;
+                        // The shaft filter assumes the ray ends at the target centroid.  A ray that
+                        // grazes its target has an ill-conditioned hit distance and may run on well
+                        // past the centroid: such a batch uses the unfiltered list.
+                        const float ex = (float)Pj.x - (float)Pi.x, ey = (float)Pj.y - (float)Pi.y,
+                                    ez = (float)Pj.z - (float)Pi.z;
+                        overshoot = tj * 1.000002f > sqrtf(ex * ex + ey * ey + ez * ez) + (1e-5f * A.scale + 1e-3f);
+                    } else {
+                        blocked = true; // the ray misses its own target: closest hit is not j
+                    }
                 }
             }
             // ---- lockstep traversal with deferred leaf tests ---------------------------
@@ -302,8 +312,10 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 // sibling subtree that holds the target (X) is not tested: its inside is
                 // covered by phase B.
                 int xref = ~tleaf;
-                for (int ks = 0; ks < nsel; ++ks) {
-                    const int e = sel_s[warp][ks];
+                const bool fullpath = __any_sync(0xffffffffu, active && overshoot);
+                const int nuse = fullpath ? npath : nsel;
+                for (int ks = 0; ks < nuse; ++ks) {
+                    const int e = fullpath ? ks : (int)sel_s[warp][ks];
                     const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
                     const int2 rg = range_s[warp][e];
                     const int ref = __float_as_int(a.w);

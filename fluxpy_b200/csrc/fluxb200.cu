@@ -37,6 +37,7 @@ struct fluxb200_mesh {
     int top_nodes_opt = 0;   // measured: L1 already serves the top of the tree (profiles/)
     int slab_limit_opt = 1 << 30;
     int blocks_per_sm = 4;
+    int shaft_filter_opt = 1;
     float ms_build = 0.f;
     float scene_h[7] = {};
 
@@ -363,6 +364,7 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.tested = M->tested.as<unsigned long long>();
     A.error_flag = M->scalars.as<int>() + 6;
     A.scale = M->scene_h[6];
+    A.shaft_filter = M->shaft_filter_opt;
     A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
@@ -1165,6 +1167,8 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->slab_limit_opt = (int)value;
             M->have_count = false;
             bvh_build(M);
+        } else if (s == "shaft_filter") {
+            M->shaft_filter_opt = value ? 1 : 0;
         } else if (s == "blocks_per_sm") {
             FB_REQUIRE(value >= 1 && value <= 8, "blocks_per_sm out of range");
             M->blocks_per_sm = (int)value;

@@ -79,15 +79,24 @@ constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 // Morton-ordered columns); every warp of the grid pulls units from one global
 // counter, consecutive units being consecutive chunks of the same row (so the
 // warps in flight share the source face and neighbouring targets).  Per unit:
+//   list     the child records hanging off the root -> source-leaf path (and
+//            off the shared part of the target side) go to shared memory once;
 //   phase 1  geometric cull: 32 coalesced float4 column loads per lane, the
-//            survivors as 32 ballot words (lane k keeps word k);
+//            survivors as 32 ballot words (lane k keeps word k); the list is
+//            then shaft-filtered against the hull of the source and the
+//            chunk's targets;
 //   phase 2  survivors are compacted 32 at a time (prefix of popcounts +
-//            find-nth-set-bit) so every lane of a batch holds a ray; the batch
-//            walks the BVH in lockstep (per-lane stack), triangles whose box
-//            and fitted slab are hit go to a per-lane list in shared memory
+//            find-nth-set-bit) so every lane of a batch holds a ray.  A: the
+//            listed records in a warp-uniform loop; B: from the target leaf
+//            upwards, the sibling record of every level; C: top-down, with a
+//            per-lane stack, only the subtrees that were hit.  Triangles whose
+//            box and fitted slab are hit go to a per-lane list in shared memory
 //            and are Pluecker-tested in a converged loop; occluded rays clear
 //            their bit in the warp's shared words;
 //   phase 3  the 32 final words go out as one coalesced 128-byte store.
+// kTop = true is the plain variant (top of the tree staged in shared memory,
+// top-down traversal from the root only); it is kept as the measured
+// alternative and as an independent check of the path walk.
 template <class T, bool kTop>
 __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs<T> A) {
     extern __shared__ float4 smem_top[];

@@ -75,9 +75,4 @@ struct HostBuf {
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
-
-// read-only 128-bit load through the non-coherent path
-__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
-
 } // namespace fluxb200

@@ -60,7 +60,6 @@ struct fluxb200_mesh {
     int64_t nnz = 0;
     bool have_count = false;
     fluxb200_ff_stats stats = {};
-    int trace_mode = 0;
 
     size_t esize() const { return dtype == FLUXB200_F64 ? 8 : 4; }
 };
@@ -1180,9 +1179,6 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
         } else if (s == "sub_rows") {
             FB_REQUIRE(value >= 1 && value <= (1 << 20), "sub_rows out of range");
             M->sub_rows_opt = (int)value;
-        } else if (s == "trace_mode") {
-            FB_REQUIRE(value == 0, "unknown trace_mode");
-            M->trace_mode = (int)value;
         } else {
             throw CudaError{"unknown option " + s};
         }

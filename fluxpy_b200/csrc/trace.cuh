@@ -1,4 +1,4 @@
-// trace.cuh -- ray set-up, Pluecker triangle test, stackless BVH traversal.
+// trace.cuh -- ray set-up, Pluecker triangle test, box + fitted-slab test, generic BVH traversal.
 //
 // Device restatement of the semantics of EmbreeTrimeshShapeModel._get_visibility
 // / _is_occluded (reference src/flux/shape.py:349-421) on Embree's robust-mode
@@ -6,7 +6,7 @@
 // test is pinned operation by operation (the "arithmetic contract"):
 // every multiply/add goes through a round-to-nearest intrinsic so nvcc cannot
 // contract or reassociate it, fused operations appear only as explicit FMAs.
-// The box test is NOT part of the contract: it only has to be conservative.
+// The box / slab test is NOT part of the contract: it only has to be conservative.
 #pragma once
 #include "common.cuh"
 #include "lbvh.cuh"

@@ -5,7 +5,7 @@ Same names, argument meaning and error behaviour as the reference
 ``TrimeshShapeModel`` (shape.py:52-258) with its four backend hooks, and the
 registry list ``trimesh_shape_models`` (shape.py:424-427).  The one backend
 here, ``CudaTrimeshShapeModel``, answers every hook from ``libfluxb200.so``
-(LBVH + stackless traversal on the B200) and adds the fused assembly hook that
+(LBVH with surface-fitted slabs + path-walk traversal on the B200) and adds the fused assembly hook that
 ``fluxpy_b200.form_factors.get_form_factor_matrix`` calls once per matrix
 instead of once per row.  No Embree, no CGAL, no CPU fallback.
 """

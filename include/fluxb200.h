@@ -198,8 +198,9 @@ int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *st
  * caller can bracket calls with its own events. */
 int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
 /* Tunables: "top_nodes" (BVH nodes staged in shared memory), "slab_limit"
- * (largest subtree, in faces, that gets a fitted slab), "blocks_per_sm", "trace_mode"
- * (0 = per-ray stackless), "sub_rows" (rows per sub-slab of fluxb200_ff_assemble). */
+ * (largest subtree, in faces, that gets a fitted slab), "blocks_per_sm" (persistent CTAs per SM of
+ * the trace kernel), "shaft_filter" (0 disables the per-unit record filter: A/B checks),
+ * "sub_rows" (rows per sub-slab of fluxb200_ff_assemble). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 
 #ifdef __cplusplus

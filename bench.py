@@ -87,9 +87,9 @@ class ClockSampler(threading.Thread):
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag = ','.join(str(i) for i in indices), [], False
 
     def run(self):
         try:
@@ -250,8 +250,11 @@ def main():
     for s in range(args.warmup):
         step_device(s)
     exchange_pending()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # one sampler for the whole box (rank 0 watches every GPU of the job): a sampler per rank
+    # means N nvidia-smi processes taking the driver lock every 100 ms inside the timed region
+    sampler = ClockSampler(range(world) if world > 1 else [local_rank]) if rank == 0 else None
+    if sampler:
+        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -271,7 +274,7 @@ def main():
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    clocks = sampler.summary()
+    clocks = sampler.summary() if sampler else None
 
     # ---- end-to-end arm: public API, host buffers in and out -----------------------------
     def step_e2e(s):

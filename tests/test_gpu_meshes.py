@@ -250,3 +250,35 @@ def test_culling_structures_are_conservative_at_scale(mods, scale):
     rows = np.array([13454, 23534, 26337, 101])
     FO = mods['oracle'].get_form_factor_matrix(om, rows)
     assert np.array_equal(np.diff(FO.indptr), ref[rows])
+
+
+def test_large_index_subsets_and_block_assembly(mods):
+    """Per-block assembly at scale (compressed_form_factors.py:550-568): many
+    chunks of non-contiguous, unsorted columns against the oracle, and the 4 x 4
+    quadrant blocks of a 10k-face crater == slices of the full matrix, bit for
+    bit (the property tests/test_compressed_form_factors.py:63-69 pins)."""
+    from fluxpy_b200 import blocks
+    V, F = mods['meshes'].gaussian_crater(159, 0, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm, om = both(mods, V, F, N)
+    rng = np.random.default_rng(7)
+    nf = sm.num_faces
+    I = rng.permutation(nf)[:160]
+    J = rng.permutation(nf)[:30000]                       # ~30 chunks, leaf positions with gaps
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, I, J),
+                    mods['oracle'].get_form_factor_matrix(om, I, J))
+    Jd = np.r_[J[:5000], J[:5000]]                         # repeated columns
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, I[:20], Jd),
+                    mods['oracle'].get_form_factor_matrix(om, I[:20], Jd))
+    V, F = mods['meshes'].gaussian_crater(72, 0, dtype=np.float64)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    full = mods['ff'].get_form_factor_matrix(sm)
+    parts = blocks.get_quadrant_order(sm.P[:, :2])
+    assert sum(len(p) for p in parts) == sm.num_faces
+    B = blocks.assemble_blocks(sm, parts)
+    for i, Iq in enumerate(parts):
+        for j, Jq in enumerate(parts):
+            S = full[Iq, :][:, Jq]
+            S.sort_indices()
+            assert B[i][j].shape == (len(Iq), len(Jq))
+            assert np.array_equal(S.indices, B[i][j].indices) and np.array_equal(S.data, B[i][j].data)

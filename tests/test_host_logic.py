@@ -178,3 +178,30 @@ print('ok')
 ''' % (ROOT, ref)
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and 'ok' in out.stdout, out.stdout + out.stderr
+
+
+def test_sharded_npz_roundtrip(tmp_path):
+    """Next row N4: per-slab scipy.sparse.save_npz files + manifest == the
+    reference's single save_npz file (collect_data.py:141)."""
+    import scipy.sparse
+    from fluxpy_b200 import io as ffio, sharded
+    rng = np.random.default_rng(0)
+    FF = scipy.sparse.random(101, 57, density=0.3, format='csr', random_state=rng, dtype=np.float32)
+    world = 4
+    starts = sharded.slab_bounds(FF.shape[0], world)
+    prefix = str(tmp_path / 'FF')
+    for r in range(world):
+        ffio.save_slab(prefix, r, world, FF[starts[r]:starts[r + 1]], starts[r], FF.shape, FF.indptr.astype(np.int64))
+    back = ffio.load_sharded(prefix)
+    assert back.shape == FF.shape and back.dtype == FF.dtype and (back != FF).nnz == 0
+    assert np.array_equal(back.indptr, FF.indptr) and np.array_equal(back.indices, FF.indices)
+    one = scipy.sparse.load_npz(ffio.slab_path(prefix, 2))        # each slab is a plain save_npz file
+    assert (one != FF[starts[2]:starts[3]]).nnz == 0
+    part = ffio.load_sharded(prefix, rows=(30, 70))
+    assert (part != FF[30:70]).nnz == 0
+    man = ffio.load_manifest(prefix)
+    assert man['nnz'] == FF.nnz and man['shape'] == [101, 57] and len(man['slabs']) == world
+    # the reference's own file for the same matrix holds the same arrays
+    scipy.sparse.save_npz(str(tmp_path / 'ref.npz'), FF)
+    ref = scipy.sparse.load_npz(str(tmp_path / 'ref.npz'))
+    assert np.array_equal(ref.data, back.data)

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 OVERFLOW = 2
 
 #: every symbol include/fluxb200.h declares
@@ -26,6 +26,7 @@ EXPORTS = (
     'fluxb200_bvh_export', 'fluxb200_ff_count', 'fluxb200_ff_fill', 'fluxb200_ff_assemble',
     'fluxb200_host_alloc', 'fluxb200_host_free', 'fluxb200_ff_device_csr', 'fluxb200_ff_detach_csr',
     'fluxb200_csr_destroy', 'fluxb200_csr_info', 'fluxb200_csr_to_host', 'fluxb200_csr_jacobi_step',
+    'fluxb200_csr_extract', 'fluxb200_csr_matmat',
     'fluxb200_visibility', 'fluxb200_is_occluded', 'fluxb200_intersect1',
     'fluxb200_visibility_bruteforce', 'fluxb200_slab_plan', 'fluxb200_mesh_stream',
     'fluxb200_set_option',
@@ -102,6 +103,8 @@ def lib():
                                     ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_float)]
     L.fluxb200_csr_to_host.argtypes = [vp, vp, vp, vp]
     L.fluxb200_csr_jacobi_step.argtypes = [vp, vp, vp, ctypes.c_double, vp, vp, ctypes.POINTER(ctypes.c_double), i64]
+    L.fluxb200_csr_extract.argtypes = [vp, vp, sz, vp, sz, pp]
+    L.fluxb200_csr_matmat.argtypes = [vp, vp, i32, vp, i32]
     L.fluxb200_ff_device_csr.argtypes = [vp, pp, pp, pp, ctypes.POINTER(i64)]
     L.fluxb200_visibility.argtypes = [vp, vp, sz, vp, sz, vp]
     L.fluxb200_visibility_bruteforce.argtypes = [vp, vp, sz, vp, sz, vp]

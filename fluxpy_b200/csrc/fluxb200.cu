@@ -11,6 +11,7 @@
 #include "lbvh.cuh"
 #include "prims.cuh"
 #include "spmv.cuh"
+#include "blockops.cuh"
 #include "trace.cuh"
 
 
@@ -1065,6 +1066,123 @@ int fluxb200_csr_jacobi_step(fluxb200_csr *C, const double *E_dev, const double 
         FB_CUDA(cudaStreamSynchronize(C->stream));
         FB_CUDA(cudaEventElapsedTime(&C->last_ms, C->ev[0], C->ev[1]));
         if (diffmax_host) memcpy(diffmax_host, &bits, sizeof(double));
+    });
+}
+
+// ---- sub-block extraction and thin dense products on a resident slab ----
+int fluxb200_csr_extract(fluxb200_csr *C, const int64_t *rows, size_t mr, const int64_t *cols, size_t nc,
+                         fluxb200_csr **out) {
+    fluxb200_csr *B = nullptr;
+    int rc = guarded([&] {
+        FB_REQUIRE(C && out && (rows || !mr) && (cols || !nc), "NULL argument");
+        FB_REQUIRE(mr < (1ull << 31) && nc < (1ull << 31), "index sets too large");
+        DeviceGuard guard(C->device);
+        std::vector<int> hrows(mr), newpos((size_t)C->n, -1);
+        for (size_t k = 0; k < mr; ++k) {
+            FB_REQUIRE(rows[k] >= 0 && rows[k] < C->m, "row index out of range");
+            hrows[k] = (int)rows[k];
+        }
+        for (size_t k = 0; k < nc; ++k) {
+            FB_REQUIRE(cols[k] >= 0 && cols[k] < C->n, "column index out of range");
+            FB_REQUIRE(newpos[(size_t)cols[k]] < 0, "repeated column index");
+            newpos[(size_t)cols[k]] = (int)k;
+        }
+        B = new fluxb200_csr();
+        B->device = C->device;
+        B->dtype = C->dtype;
+        B->index_width = C->index_width;
+        B->m = (int64_t)mr;
+        B->n = (int64_t)nc;
+        FB_CUDA(cudaStreamCreateWithFlags(&B->stream, cudaStreamNonBlocking));
+        for (auto &e : B->ev) FB_CUDA(cudaEventCreate(&e));
+        cudaStream_t st = C->stream;
+        DevBuf drows, dnew, dcounts;
+        drows.reserve(sizeof(int) * std::max<size_t>(mr, 1));
+        dnew.reserve(sizeof(int) * std::max<size_t>((size_t)C->n, 1));
+        dcounts.reserve(sizeof(int64_t) * std::max<size_t>(mr, 1));
+        B->indptr.reserve(sizeof(int64_t) * (mr + 1));
+        if (mr) FB_CUDA(cudaMemcpyAsync(drows.p, hrows.data(), sizeof(int) * mr, cudaMemcpyHostToDevice, st));
+        if (C->n) FB_CUDA(cudaMemcpyAsync(dnew.p, newpos.data(), sizeof(int) * (size_t)C->n, cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemsetAsync(B->indptr.p, 0, sizeof(int64_t) * (mr + 1), st));
+        FB_CUDA(cudaEventRecord(C->ev[0], st));
+        if (mr) {
+            if (C->index_width == 4)
+                extract_count_kernel<int32_t><<<(unsigned)mr, kBlockThreads, 0, st>>>(
+                    C->indptr.as<int64_t>(), C->indices.as<int32_t>(), drows.as<int>(), (int)mr, dnew.as<int>(),
+                    dcounts.as<int64_t>());
+            else
+                extract_count_kernel<int64_t><<<(unsigned)mr, kBlockThreads, 0, st>>>(
+                    C->indptr.as<int64_t>(), C->indices.as<int64_t>(), drows.as<int>(), (int)mr, dnew.as<int>(),
+                    dcounts.as<int64_t>());
+            scan_exclusive<int64_t, int64_t>(dcounts.as<int64_t>(), B->indptr.as<int64_t>(), (int64_t)mr,
+                                             B->indptr.as<int64_t>() + mr, st);
+        }
+        int64_t nnz = 0;
+        FB_CUDA(cudaMemcpyAsync(&nnz, B->indptr.as<int64_t>() + mr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        FB_CUDA(cudaStreamSynchronize(st));
+        B->nnz = nnz;
+        const size_t es = C->dtype == FLUXB200_F64 ? 8 : 4;
+        B->indices.reserve((size_t)C->index_width * std::max<int64_t>(nnz, 1));
+        B->data.reserve(es * std::max<int64_t>(nnz, 1));
+        if (mr && nnz) {
+#define FB_EXTRACT(TT, II)                                                                                     \
+    extract_fill_kernel<TT, II><<<(unsigned)mr, kBlockThreads, 0, st>>>(                                       \
+        C->indptr.as<int64_t>(), C->indices.as<II>(), C->data.as<TT>(), drows.as<int>(), (int)mr, dnew.as<int>(), \
+        B->indptr.as<int64_t>(), B->indices.as<II>(), B->data.as<TT>())
+            if (C->dtype == FLUXB200_F64) {
+                if (C->index_width == 4) FB_EXTRACT(double, int32_t);
+                else FB_EXTRACT(double, int64_t);
+            } else {
+                if (C->index_width == 4) FB_EXTRACT(float, int32_t);
+                else FB_EXTRACT(float, int64_t);
+            }
+#undef FB_EXTRACT
+            FB_CUDA(cudaGetLastError());
+        }
+        FB_CUDA(cudaEventRecord(C->ev[1], st));
+        FB_CUDA(cudaStreamSynchronize(st));
+        FB_CUDA(cudaEventElapsedTime(&C->last_ms, C->ev[0], C->ev[1]));
+        drows.release();
+        dnew.release();
+        dcounts.release();
+        *out = B;
+    });
+    if (rc && B) fluxb200_csr_destroy(B);
+    return rc;
+}
+
+int fluxb200_csr_matmat(fluxb200_csr *C, const double *X_dev, int k, double *Y_dev, int transpose) {
+    return guarded([&] {
+        FB_REQUIRE(C && X_dev && Y_dev, "NULL argument");
+        FB_REQUIRE(k >= 1 && k <= 32, "matmat: 1 <= k <= 32 right-hand sides per call");
+        DeviceGuard guard(C->device);
+        cudaStream_t st = C->stream;
+        FB_CUDA(cudaEventRecord(C->ev[0], st));
+        if (transpose) FB_CUDA(cudaMemsetAsync(Y_dev, 0, sizeof(double) * (size_t)C->n * k, st));
+        if (C->m) {
+            const unsigned grid = (unsigned)C->m;
+#define FB_MM(KERNEL, TT, II)                                                                          \
+    KERNEL<TT, II><<<grid, kBlockThreads, 0, st>>>(C->indptr.as<int64_t>(), C->indices.as<II>(),       \
+                                                   C->data.as<TT>(), (int)C->m, X_dev, k, Y_dev)
+#define FB_MM_DISPATCH(KERNEL)                                  \
+    do {                                                        \
+        if (C->dtype == FLUXB200_F64) {                         \
+            if (C->index_width == 4) FB_MM(KERNEL, double, int32_t); \
+            else FB_MM(KERNEL, double, int64_t);                \
+        } else {                                                \
+            if (C->index_width == 4) FB_MM(KERNEL, float, int32_t);  \
+            else FB_MM(KERNEL, float, int64_t);                 \
+        }                                                       \
+    } while (0)
+            if (transpose) FB_MM_DISPATCH(csr_rmatmat_kernel);
+            else FB_MM_DISPATCH(csr_matmat_kernel);
+#undef FB_MM_DISPATCH
+#undef FB_MM
+            FB_CUDA(cudaGetLastError());
+        }
+        FB_CUDA(cudaEventRecord(C->ev[1], st));
+        FB_CUDA(cudaStreamSynchronize(st));
+        FB_CUDA(cudaEventElapsedTime(&C->last_ms, C->ev[0], C->ev[1]));
     });
 }
 

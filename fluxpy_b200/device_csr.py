@@ -80,6 +80,42 @@ class DeviceCsrSlab:
 
     __matmul__ = matvec
 
+    def extract(self, rows, cols):
+        """``self[rows, :][:, cols]`` as a new device-resident slab
+        (src/flux/compressed_form_factors.py:562).  ``rows``: local row numbers,
+        ``cols``: column positions without repeats."""
+        rows = np.ascontiguousarray(np.asarray(rows).astype(np.int64))
+        cols = np.ascontiguousarray(np.asarray(cols).astype(np.int64))
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().fluxb200_csr_extract(self._h, _lib.ptr(rows), len(rows), _lib.ptr(cols), len(cols),
+                                                   ctypes.byref(h)))
+        return DeviceCsrSlab(h, self.device)
+
+    def _thin_product(self, X, transpose):
+        torch, dev = self._torch()
+        m, n = self.shape
+        rows_in, rows_out = (m, n) if transpose else (n, m)
+        X = X.to(torch.float64)
+        assert X.is_cuda and X.dim() == 2 and X.shape[0] == rows_in
+        Y = torch.empty(rows_out, X.shape[1], dtype=torch.float64, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        for c0 in range(0, X.shape[1], 32):            # the kernel takes up to 32 right-hand sides
+            Xc = X[:, c0:c0 + 32].contiguous()
+            Yc = torch.empty(rows_out, Xc.shape[1], dtype=torch.float64, device=dev)
+            torch.cuda.current_stream(dev).synchronize()
+            _lib.check(_lib.lib().fluxb200_csr_matmat(self._h, Xc.data_ptr(), Xc.shape[1], Yc.data_ptr(),
+                                                      1 if transpose else 0))
+            Y[:, c0:c0 + 32] = Yc
+        return Y
+
+    def matmat(self, X):
+        """``A @ X`` for a thin dense float64 CUDA tensor ``X`` (n x k)."""
+        return self._thin_product(X, False)
+
+    def rmatmat(self, X):
+        """``A.T @ X`` for a thin dense float64 CUDA tensor ``X`` (m x k)."""
+        return self._thin_product(X, True)
+
     def to_scipy(self):
         """Download as ``scipy.sparse.csr_matrix`` (tests / small matrices)."""
         import scipy.sparse

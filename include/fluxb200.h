@@ -34,7 +34,7 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 3
+#define FLUXB200_ABI_VERSION 4
 
 #define FLUXB200_OK 0
 #define FLUXB200_ERROR 1
@@ -159,6 +159,21 @@ int fluxb200_csr_to_host(fluxb200_csr *csr, void *indptr, void *indices, void *d
 int fluxb200_csr_jacobi_step(fluxb200_csr *csr, const double *E_dev, const double *rho_dev,
                              double rho_scalar, const double *x_dev, double *y_dev,
                              double *diffmax_host, int64_t row_offset);
+
+/* ---- feeding the hierarchical compression from the resident slab (next row N3) -- */
+
+/* out = src[rows, :][:, cols]: the CSR slicing FormFactor2dTreeBlock does on the
+ * parent's matrix (src/flux/compressed_form_factors.py:562).  rows: local row
+ * numbers of the slab (any order, may repeat); cols: column positions of src,
+ * without repeats; the new column ids are positions into `cols`, entries keep
+ * the source order (ascending when cols is ascending). */
+int fluxb200_csr_extract(fluxb200_csr *src, const int64_t *rows, size_t mr, const int64_t *cols,
+                         size_t nc, fluxb200_csr **out);
+/* Thin dense products, DEVICE pointers to row-major float64, 1 <= k <= 32:
+ * transpose == 0:  Y[m x k] = A @ X[n x k];   transpose != 0:  Y[n x k] = A^T @ X[m x k].
+ * The two products of a randomised range finder for the SVD leaves
+ * (src/flux/compressed_form_factors.py:388-405, src/flux/linalg.py:8-50). */
+int fluxb200_csr_matmat(fluxb200_csr *csr, const double *X_dev, int k, double *Y_dev, int transpose);
 
 /* ---- TrimeshShapeModel hooks (src/flux/shape.py:129-188, 349-421) ---------- */
 

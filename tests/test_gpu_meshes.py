@@ -282,3 +282,56 @@ def test_large_index_subsets_and_block_assembly(mods):
             S.sort_indices()
             assert B[i][j].shape == (len(Iq), len(Jq))
             assert np.array_equal(S.indices, B[i][j].indices) and np.array_equal(S.data, B[i][j].data)
+
+
+def test_block_extraction_and_lowrank_feed(mods):
+    """Next row N3: device-side spmat[row_inds, :][:, col_inds]
+    (compressed_form_factors.py:562) == SciPy slicing bit for bit; thin products
+    A@X, A.T@X == SciPy; randomised truncated SVD of an off-diagonal quadrant
+    block == scipy.sparse.linalg.svds (what linalg.py:8-18 calls)."""
+    import scipy.sparse.linalg
+    import torch
+    from fluxpy_b200 import blocks, lowrank, get_form_factor_matrix_device
+    V, F = mods['meshes'].gaussian_crater(40, 2, dtype=np.float32)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    FFd = get_form_factor_matrix_device(sm)
+    FFh = FFd.to_scipy()
+    parts = blocks.get_quadrant_order(sm.P[:, :2])
+    for (i, j) in ((0, 3), (1, 1), (2, 0)):
+        B = FFd.extract(parts[i], parts[j])
+        S = FFh[parts[i], :][:, parts[j]]
+        S.sort_indices()
+        Bh = B.to_scipy()
+        assert Bh.shape == S.shape and np.array_equal(Bh.indptr, S.indptr)
+        assert np.array_equal(Bh.indices, S.indices) and np.array_equal(Bh.data, S.data)
+    # unsorted / repeated rows, unsorted columns: same content as SciPy after sorting
+    rng = np.random.default_rng(2)
+    rows = rng.integers(0, FFh.shape[0], 200)
+    cols = rng.permutation(FFh.shape[1])[:700]
+    Bh = FFd.extract(rows, cols).to_scipy()
+    S = FFh[rows, :][:, cols]
+    assert (Bh != S).nnz == 0 and Bh.nnz == S.nnz
+    empty = FFd.extract([], cols)
+    assert empty.shape == (0, 700) and empty.nnz == 0
+    with pytest.raises(RuntimeError):
+        FFd.extract([0], [3, 3])
+    # thin products
+    B = FFd.extract(parts[0], parts[3])
+    Bh = B.to_scipy().astype(np.float64)
+    X = rng.normal(size=(Bh.shape[1], 40))
+    Y = B.matmat(torch.as_tensor(X, device='cuda')).cpu().numpy()
+    assert np.allclose(Y, Bh@X, rtol=1e-12, atol=1e-14)
+    Z = rng.normal(size=(Bh.shape[0], 7))
+    W = B.rmatmat(torch.as_tensor(Z, device='cuda')).cpu().numpy()
+    assert np.allclose(W, Bh.T@Z, rtol=1e-11, atol=1e-13)
+    # truncated SVD of the (numerically low-rank) far-field block
+    k = 12
+    U, Sg, Vt = lowrank.sparse_svd(B, k)
+    Sref = np.sort(scipy.sparse.linalg.svds(Bh, k, return_singular_vectors=False))[::-1]
+    assert np.allclose(Sg, Sref, rtol=1e-6)
+    assert U.shape == (Bh.shape[0], k) and Vt.shape == (k, Bh.shape[1])
+    approx = (U*Sg)@Vt
+    err = np.linalg.norm(Bh.toarray() - approx, 2)
+    assert err <= 1.05*np.linalg.svd(Bh.toarray(), compute_uv=False)[k] + 1e-12
+    out = lowrank.estimate_rank(B, 1e-2)
+    assert out is not None and 1 <= out[1].size <= min(Bh.shape) and out[1][-1] >= 1e-2*out[1][0]

@@ -286,8 +286,10 @@ def main():
         else:
             FF = fluxpy_b200.get_form_factor_matrix(sm, rows, None, EPS)
         st = form_factors.last_stats if world == 1 else res.stats
-        d2h = FF.data.nbytes + FF.indices.nbytes + FF.indptr.nbytes
-        h2d = rows.nbytes + sm.P.nbytes + sm.N.nbytes + sm.A.nbytes
+        # bytes the library actually moved (its own count): the CSR values + the visibility words
+        # the column indices are expanded from on the host + row counts; index set + face arrays in
+        d2h = st['d2h_bytes']
+        h2d = st['h2d_bytes'] + sm.P.nbytes + sm.N.nbytes + sm.A.nbytes
         chk = float(FF.data[:16].sum())                  # touch the result on the host
         return st, h2d, d2h, chk
 

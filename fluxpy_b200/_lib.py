@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 OVERFLOW = 2
 
 #: every symbol include/fluxb200.h declares
@@ -29,7 +29,7 @@ EXPORTS = (
     'fluxb200_csr_extract', 'fluxb200_csr_matmat',
     'fluxb200_visibility', 'fluxb200_is_occluded', 'fluxb200_intersect1',
     'fluxb200_visibility_bruteforce', 'fluxb200_slab_plan', 'fluxb200_mesh_stream',
-    'fluxb200_set_option',
+    'fluxb200_set_option', 'fluxb200_expand_words',
 )
 
 
@@ -38,7 +38,8 @@ class FFStats(ctypes.Structure):
                 ('nnz', ctypes.c_int64), ('ms_prepare', ctypes.c_float),
                 ('ms_trace', ctypes.c_float), ('ms_scan', ctypes.c_float),
                 ('ms_fill', ctypes.c_float), ('ms_d2h', ctypes.c_float),
-                ('trace_launches', ctypes.c_int32), ('kernel_launches', ctypes.c_int32)]
+                ('trace_launches', ctypes.c_int32), ('kernel_launches', ctypes.c_int32),
+                ('h2d_bytes', ctypes.c_int64), ('d2h_bytes', ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -114,6 +115,7 @@ def lib():
     L.fluxb200_slab_plan.argtypes = [sz, i32, vp, vp]
     L.fluxb200_mesh_stream.argtypes = [vp, pp]
     L.fluxb200_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    L.fluxb200_expand_words.argtypes = [vp, sz, i32, vp, ctypes.POINTER(i64)]
     for name in EXPORTS:
         if name != 'fluxb200_last_error' and name != 'fluxb200_abi_version':
             getattr(L, name).restype = i32

@@ -301,19 +301,26 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                     }
                 }
             }
-            // ---- lockstep traversal with deferred leaf tests ---------------------------
+            // ---- traversal with deferred leaf tests -----------------------------------
+            // Every lane walks its own ray (no votes inside the loops: lanes that finish a
+            // phase early wait at its end).  Triangles whose box and fitted slab are hit go
+            // to a per-lane list in shared memory and are Pluecker-tested by the whole warp
+            // in one converged loop at the end of the batch; a lane whose list is full
+            // tests the newcomer on the spot (rare).
             const RayBox rb = make_raybox(ray);
             const float tmax = tj * 1.000002f;
             int stack[kStackDepth];
             int sp = 0, node = 0, nl = 0;
-            auto flush = [&]() {
-                int mx = nl;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                for (int q = 0; q < mx; ++q)
-                    if (q < nl && !blocked) blocked = leaf_occludes(bvh, ray, tj, leaf_s[q][tid], tface);
-                nl = 0;
-                if (blocked) active = false;
+            auto push_leaf = [&](int leaf) {
+                if (nl < kLeafCap) leaf_s[nl++][tid] = leaf;
+                else if (leaf_occludes_cold(A.tri, ray, tj, leaf, tface)) {
+                    blocked = true;
+                    active = false;
+                }
+            };
+            auto push_node = [&](int ref) {
+                if (sp < kStackDepth) stack[sp++] = ref;
+                else *A.error_flag = 1;
             };
             // (the tree depth was checked against kStackDepth when it was built)
             if (!kTop) {
@@ -331,31 +338,26 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                     if (tleaf >= rg.x && tleaf <= rg.y) {
                         xref = ref;
                     } else if (active && child_hit(ray, rb, a, b, cc, tmax)) {
-                        if (ref < 0) leaf_s[nl++][tid] = ~ref;
-                        else if (sp < kStackDepth) stack[sp++] = ref;
-                        else *A.error_flag = 1;
+                        if (ref < 0) push_leaf(~ref);
+                        else push_node(ref);
                     }
-                    if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
                 }
-                // phase B: from the target leaf up to X, the sibling at every level
-                // (one record per level instead of a two-child node per level from the root)
+                // phase B: from the target leaf up to X (or the chunk's common ancestor), the
+                // sibling at every level -- one 48-byte record per level instead of a two-child
+                // node per level from the root.  `code` = (parent << 1 | my slot), so the
+                // sibling is record code ^ 1 of the node array.
                 const int stop = cref != -0x7fffffff ? cref : xref;
                 int cur = ~tleaf, code = tleaf >= 0 ? A.leaf_up[tleaf] : -1;
-                while (__any_sync(0xffffffffu, active && cur != stop && code >= 0)) {
-                    if (active && cur != stop && code >= 0) {
-                        const int p = code >> 1, slot = code & 1;
-                        const float4 *rec = A.nodes + 6 * (size_t)p + 3 * (1 - slot);
-                        const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
-                        code = A.node_up[p];
-                        cur = p;
-                        if (child_hit(ray, rb, a, b, cc, tmax)) {
-                            const int ref = __float_as_int(a.w);
-                            if (ref < 0) leaf_s[nl++][tid] = ~ref;
-                            else if (sp < kStackDepth) stack[sp++] = ref;
-                            else *A.error_flag = 1;
-                        }
+                while (active && cur != stop && code >= 0) {
+                    const float4 *rec = A.nodes + 3 * (size_t)(unsigned)(code ^ 1);
+                    const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
+                    cur = code >> 1;
+                    code = A.node_up[cur];
+                    if (child_hit(ray, rb, a, b, cc, tmax)) {
+                        const int ref = __float_as_int(a.w);
+                        if (ref < 0) push_leaf(~ref);
+                        else push_node(ref);
                     }
-                    if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
                 }
                 // phase C: the subtrees that were actually hit, top-down
                 if (active) {
@@ -363,26 +365,29 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                     else active = false;
                 }
             }
-            while (__any_sync(0xffffffffu, active)) {
-                if (active) {
-                    float4 q[6];
-                    load_node<kTop>(bvh, node, q);
-                    const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
-                    const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
-                    const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
-                    if (h0 && r0 < 0 && ~r0 != tleaf) leaf_s[nl++][tid] = ~r0;
-                    if (h1 && r1 < 0 && ~r1 != tleaf) leaf_s[nl++][tid] = ~r1;
-                    const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
-                    if (i0 && i1) stack[sp++] = r1;
-                    node = i0 ? r0 : r1;
-                    if (!(i0 || i1)) {
-                        if (sp > 0) node = stack[--sp];
-                        else active = false;
-                    }
+            while (active) {
+                float4 q[6];
+                load_node<kTop>(bvh, node, q);
+                const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
+                const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
+                const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                if (h0 && r0 < 0 && ~r0 != tleaf) push_leaf(~r0);
+                if (h1 && r1 < 0 && ~r1 != tleaf) push_leaf(~r1);
+                const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
+                if (i0 && i1) stack[sp++] = r1;
+                node = i0 ? r0 : r1;
+                if (!(i0 || i1)) {
+                    if (sp > 0) node = stack[--sp];
+                    else active = false;
                 }
-                if (__any_sync(0xffffffffu, nl > kLeafCap - 2)) flush();
             }
-            flush();
+            { // converged exact tests of the listed candidates
+                int mx = nl;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                for (int q = 0; q < mx; ++q)
+                    if (q < nl && !blocked) blocked = leaf_occludes(bvh, ray, tj, leaf_s[q][tid], tface);
+            }
             if (blocked) atomicAnd(&words_s[warp][k], ~(1u << bit));
         }
         __syncwarp();
@@ -400,107 +405,180 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
 }
 
 // ---------------------------------------------------------------------------
-// K6: CSR fill.  One CTA per row; columns are visited in ORIGINAL J order so
-// every row comes out with ascending column positions (form_factors.py:52,
-// 69).  The row's visibility words (sorted-column order) are staged in shared
-// memory and looked up through rank_of_pos.  Each warp owns a contiguous
-// segment of the columns: one counting pass, one block-wide prefix over the 8
-// warp totals (the only barrier), one writing pass.
+// K6: CSR fill in two kernels.  K4 leaves the visibility words of a row in
+// sorted-column (BVH-leaf) order; the CSR wants the caller's column order with
+// ascending positions (form_factors.py:52, 69).
+//
+// K6a un-permutes: one CTA stages R rows of leaf-order words in shared memory
+// and reads rank_of_pos once per column for all R rows (the permutation is the
+// same for every row), so the m*n lookups are shared-memory reads; 32 ballots
+// give each lane one J-order word, stored coalesced.
+// K6b emits: one CTA per 8 rows (a warp each).  Per group of 1024 columns the CTA
+// gathers the columns' P, N, A into shared memory once for its 8 rows; the lanes
+// of a warp expand the set bits of their word of the row into a list of column
+// positions, then the warp walks that list 32 entries at a time -- every lane
+// computes one stored entry (no lanes idling on zeros) and data / indices go out
+// as consecutive, coalesced stores.  Values are recomputed in fp64 and rounded
+// once to the model dtype (form_factors.py:62-64).
 // ---------------------------------------------------------------------------
 constexpr int kFillThreads = 256;
+constexpr int kFillWarps = kFillThreads / 32;
+
+// kSmem = false (R = 1): rows too long for shared memory are looked up in global memory
+template <int R, bool kSmem>
+__global__ void __launch_bounds__(kFillThreads)
+unpermute_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ rank_of_pos, int m, int n,
+                 int nwords, uint32_t *__restrict__ jbits, uint32_t *__restrict__ gcount) {
+    extern __shared__ uint32_t rows_smem[]; // R x nwords, leaf order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row0 = blockIdx.x * R;
+    const int nr = min(R, m - row0);
+    const uint32_t *rows_s = kSmem ? rows_smem : bits + (size_t)row0 * nwords;
+    if (kSmem) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            uint32_t *dst = rows_smem + (size_t)r * nwords;
+            const uint32_t *src = bits + (size_t)(row0 + r) * nwords;
+            for (int k = threadIdx.x; k < nwords; k += kFillThreads) dst[k] = r < nr ? src[k] : 0u;
+        }
+        __syncthreads();
+    }
+    const int ngroups = (nwords + 31) / 32;
+    for (int g = warp; g < ngroups; g += kFillWarps) {
+        uint32_t mine[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) mine[r] = 0u;
+        const int q0 = g * 1024;
+        const int tiles = min(32, (n - q0 + 31) / 32);
+        for (int t0 = 0; t0 < tiles; t0 += 8) {
+            int s[8]; // eight independent loads of the permutation in flight per lane
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + (t0 + u) * 32 + lane;
+                s[u] = (t0 + u < tiles && q < n) ? __ldg(rank_of_pos + q) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const bool set = s[u] >= 0 && ((rows_s[(size_t)r * nwords + (s[u] >> 5)] >> (s[u] & 31)) & 1u);
+                    const uint32_t w = __ballot_sync(0xffffffffu, set);
+                    if (lane == t0 + u) mine[r] = w;
+                }
+            }
+        }
+        const int wi = g * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r < nr) { // warp-uniform
+                if (wi < nwords) jbits[(size_t)(row0 + r) * nwords + wi] = mine[r];
+                uint32_t c = __popc(mine[r]);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                if (lane == 0) gcount[(size_t)(row0 + r) * ngroups + g] = c;
+            }
+        }
+    }
+}
 
 template <class T> struct FillArgs {
     const Real4<T> *faceP, *faceN;
     const int *rows;        // m
     const int *cols;        // n face ids in original J order
-    const int *rank_of_pos; // n: sorted position of original column q
     int m, n, nwords;
-    const uint32_t *bits;
+    const uint32_t *jbits;  // m x nwords visibility words, ORIGINAL column order
+    const uint32_t *gcount; // m x ceil(nwords/32) entries per (row, group of 1024 columns)
     const int64_t *indptr;  // m + 1 (device, int64), local to this launch's rows
     int64_t out_base;       // position of row 0's first entry in data / indices
     T *data;
-    void *indices;          // int32 or int64
+    void *indices;          // int32 or int64; NULL: the caller expands jbits itself
     int index_width;
-    int bits_in_smem;
 };
 
+// One CTA = 8 consecutive rows (one per warp) x one segment of the column groups (blockIdx.y; the
+// row's entry count before the segment comes from K6a's per-group counts).  Per group of 1024 columns the CTA
+// gathers P, N, A of the group's columns into shared memory once (the gather through `cols` and
+// the L2 reads are shared by the 8 rows), then every warp emits its row's entries of the group.
+constexpr int kFillGroup = 1024;
+template <class T> constexpr size_t emit_smem_bytes() { return 2 * sizeof(Real4<T>) * kFillGroup; }
+
 template <class T>
-__global__ void __launch_bounds__(kFillThreads) fill_kernel(const FillArgs<T> A) {
-    extern __shared__ uint32_t bits_s[];
-    __shared__ uint32_t warp_tot[kFillThreads / 32];
-    const int r = blockIdx.x;
+__global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char stage_raw[];
+    Real4<T> *colP_s = reinterpret_cast<Real4<T> *>(stage_raw), *colN_s = colP_s + kFillGroup;
+    __shared__ int colj_s[kFillGroup];
+    __shared__ uint16_t list_s[kFillWarps][kFillGroup];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row_begin = A.out_base + A.indptr[r];
-    if (A.indptr[r + 1] == A.indptr[r]) return;
-    const uint32_t *gbits = A.bits + (size_t)r * A.nwords;
-    if (A.bits_in_smem) {
-        for (int k = threadIdx.x; k < A.nwords; k += kFillThreads) bits_s[k] = gbits[k];
-        __syncthreads();
-    }
-    const uint32_t *bits = A.bits_in_smem ? bits_s : gbits;
-    // every warp owns one contiguous segment of the ORIGINAL column order (multiple of 32 columns)
-    const int groups = (A.n + 31) / 32;
-    const int gper = (groups + kFillThreads / 32 - 1) / (kFillThreads / 32);
-    const int q_begin = min(A.n, warp * gper * 32), q_end = min(A.n, (warp + 1) * gper * 32);
-    // pass 1: entries in my segment (four independent lookups in flight per lane)
-    constexpr int U = 4;
-    uint32_t cnt = 0;
-    for (int q0 = q_begin; q0 < q_end; q0 += 32 * U) {
-        int sidx[U];
+    const int r = blockIdx.x * kFillWarps + warp;
+    // blockIdx.y = segment of the column groups (enough CTAs for a small row slab)
+    const int ngroups = (A.nwords + 31) / 32;
+    const int gper = (ngroups + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int g_begin = blockIdx.y * gper, g_end = min(ngroups, g_begin + gper);
+    if (g_begin >= g_end) return;
+    const bool live = r < A.m && A.indptr[r + 1] != A.indptr[r];
+    const uint32_t *jb = A.jbits + (size_t)(live ? r : 0) * A.nwords;
+    int64_t off = 0;
+    if (live) { // entries of the row before my segment
+        uint32_t before = 0;
+        for (int g = lane; g < g_begin; g += 32) before += A.gcount[(size_t)r * ngroups + g];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int q = q0 + u * 32 + lane;
-            sidx[u] = q < q_end ? A.rank_of_pos[q] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool set = sidx[u] >= 0 && ((bits[sidx[u] >> 5] >> (sidx[u] & 31)) & 1u);
-            cnt += __popc(__ballot_sync(0xffffffffu, set));
-        }
+        for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        off = A.out_base + A.indptr[r] + before;
     }
-    if (lane == 0) warp_tot[warp] = cnt;
-    __syncthreads();
-    uint32_t off = 0;
-    for (int w = 0; w < warp; ++w) off += warp_tot[w];
-    // pass 2: values (fp64, rounded once) and column positions, in ascending order
-    const int i = A.rows[r];
+    const int i = live ? A.rows[r] : 0;
     const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
-    for (int q0 = q_begin; q0 < q_end; q0 += 32 * U) {
-        int sidx[U], jj[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int q = q0 + u * 32 + lane;
-            sidx[u] = q < q_end ? A.rank_of_pos[q] : -1;
-            jj[u] = q < q_end ? A.cols[q] : 0;
-        }
-        bool set[U];
-        Real4<T> Pj[U], Nj[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            set[u] = sidx[u] >= 0 && ((bits[sidx[u] >> 5] >> (sidx[u] & 31)) & 1u);
-            if (set[u]) {
-                Pj[u] = load_real4<T>(A.faceP + jj[u]);
-                Nj[u] = load_real4<T>(A.faceN + jj[u]);
+    for (int g = g_begin; g < g_end; ++g) {
+        __syncthreads(); // the previous group's columns are no longer read
+        for (int c = threadIdx.x; c < kFillGroup; c += kFillThreads) {
+            const int q = g * kFillGroup + c;
+            if (q < A.n) {
+                const int j = A.cols[q];
+                colj_s[c] = j;
+                colP_s[c] = load_real4<T>(A.faceP + j);
+                colN_s[c] = load_real4<T>(A.faceN + j);
             }
         }
+        __syncthreads();
+        if (!live) continue;
+        const int wi = g * 32 + lane;
+        uint32_t word = wi < A.nwords ? jb[wi] : 0u;
+        const int c = __popc(word);
+        int incl = c;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, set[u]);
-            if (set[u]) {
-                double dx, dy, dz;
-                double num = numerator<T>(Pi, Ni, Pj[u], Nj[u], dx, dy, dz);
-                if (jj[u] == i) num = 0.0;
-                const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
-                const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                 // :62
-                const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj[u].w), sden); // :63-64
-                const int64_t dst = row_begin + off + __popc(bal & ((1u << lane) - 1u));
-                A.data[dst] = (T)v;
-                const int q = q0 + u * 32 + lane;
-                if (A.index_width == 4) reinterpret_cast<int32_t *>(A.indices)[dst] = q;
-                else reinterpret_cast<int64_t *>(A.indices)[dst] = q;
-            }
-            off += __popc(bal);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        int p = incl - c;
+        while (word) { // ascending positions of my word's set bits
+            list_s[warp][p++] = (uint16_t)(lane * 32 + (__ffs(word) - 1));
+            word &= word - 1;
+        }
+        __syncwarp();
+        for (int e = lane; e < total; e += 32) {
+            const int cpos = (int)list_s[warp][e];
+            const int j = colj_s[cpos];
+            const Real4<T> Pj = colP_s[cpos], Nj = colN_s[cpos];
+            double dx, dy, dz;
+            double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
+            if (j == i) num = 0.0;
+            const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
+            const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                           // :62
+            const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj.w), sden); // :63-64
+            const int64_t dst = off + e;
+            // streaming stores: the CSR is written once and must not push the mesh and BVH, which a
+            // concurrently running trace kernel lives on, out of L2
+            __stcs(A.data + dst, (T)v);
+            const int q = g * kFillGroup + cpos;
+            if (A.indices) {
+                if (A.index_width == 4) __stcs(reinterpret_cast<int *>(A.indices) + dst, q);
+                else __stcs(reinterpret_cast<long long *>(A.indices) + dst, (long long)q);
+            }
+        }
+        __syncwarp();
+        off += total;
     }
 }
 
@@ -634,6 +712,17 @@ __global__ void unpack_face_kernel(const Real4<T> *__restrict__ faceP, const Rea
 __global__ void counts_to_i64_kernel(const uint32_t *__restrict__ c, int m, int64_t *__restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < m) out[r] = (int64_t)c[r];
+}
+
+// Row counts and the sub-slab's entry count straight into page-locked host memory (zero-copy
+// stores): a cudaMemcpy of a few KB would queue on the copy engine behind the previous sub-slab's
+// multi-megabyte copy-out and stall the host loop that waits for these numbers.
+__global__ void publish_counts_kernel(const uint32_t *__restrict__ c, int m, const int64_t *__restrict__ total,
+                                      uint32_t *host_counts, int64_t *host_total) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) host_counts[r] = c[r];
+    if (r == 0) *host_total = *total;
+    __threadfence_system();
 }
 
 __global__ void indptr_to_i32_kernel(const int64_t *__restrict__ in, int n, int32_t *__restrict__ out) {

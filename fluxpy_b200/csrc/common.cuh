@@ -62,7 +62,7 @@ struct HostBuf {
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        FB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+        FB_CUDA(cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped)); // kernels may store into it
         cap = want;
     }
     void release() {

@@ -3,7 +3,10 @@
 // enqueued on the handle's own stream.
 #include "../../include/fluxb200.h"
 #include <algorithm>
+#include <chrono>
 #include <functional>
+#include <memory>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "assemble.cuh"
@@ -13,6 +16,7 @@
 #include "spmv.cuh"
 #include "blockops.cuh"
 #include "trace.cuh"
+#include "host_expand.h"
 
 
 namespace fluxb200 {
@@ -44,17 +48,29 @@ struct fluxb200_mesh {
 
     // per-call state
     DevBuf rows, cols, ckeys, cvals, colP, colN, col_face, col_leaf, rank_of_pos, bits, row_counts,
-        counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout;
+        counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout, jbits;
     // streaming assembly (double-buffered sub-slabs, second stream for fill + D2H)
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // fill kernels
+    cudaStream_t d2h_stream = nullptr;  // copy-out (its own stream: fill(k+1) must not queue behind D2H(k))
     static constexpr int kSlots = 3;
     cudaEvent_t slot_free[kSlots] = {};
+    cudaEvent_t d2h_done[kSlots] = {};
     std::vector<cudaEvent_t> sub_events;
-    DevBuf sbits[kSlots], scounts[kSlots], scounts64[kSlots], sindptr[kSlots], stage_data[kSlots], stage_idx[kSlots];
+    std::vector<cudaEvent_t> tl_events; // FLUXB200_TIMELINE: fill / copy-out brackets per sub-slab
+    DevBuf sbits[kSlots], scounts[kSlots], scounts64[kSlots], sindptr[kSlots], stage_data[kSlots], stage_idx[kSlots],
+        sjbits[kSlots];
     HostBuf h_nnz, h_counts;
     int64_t dev_capacity_hint = 0;
     int out_index_width = 0; // index width of the library-owned device CSR (0: none)
     int sub_rows_opt = 512;
+    // host copy-out: ship the J-order visibility words instead of the column indices and let a few
+    // host threads write the indices (host_expand.cpp)
+    static constexpr int kHostSlots = 8; // ring of page-locked word buffers (sub-slabs in flight on the host)
+    HostBuf h_jbits;
+    HostExpander expander;
+    int host_expand_opt = 1;
+    int host_threads_opt = 0; // 0 = automatic
+    int fill_rows_opt = 0;   // rows per CTA of the un-permute kernel: 0 = as many as fit, -1 = no shared memory
     size_t m = 0, n = 0;
     int nwords = 0;
     double eps = 0;
@@ -305,6 +321,7 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
     M->nwords = (int)ceil_div((int64_t)n, 32);
     int launches = 0;
     upload_index_sets(M, I, m, J, n);
+    M->stats.h2d_bytes = (int64_t)(sizeof(int) * (m + n));
     M->tested.reserve(sizeof(unsigned long long) * 2);
     FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 2, st));
     if (m && n) {
@@ -381,33 +398,68 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     FB_CUDA(cudaGetLastError());
 }
 
-// K6 for rows [row0, row0 + mr): local indptr (mr + 1) -> data / indices at out_base
+// K6 for rows [row0, row0 + mr): local indptr (mr + 1) -> data / indices at out_base.
+// K6a (un-permute R rows per CTA into `jbits`, J-order words) then K6b (emit).  `jbits`
+// is a scratch of the stream the call is enqueued on, or the caller's own buffer when it
+// wants the J-order words as a result (indices == NULL: the host expands them).
+template <int R, bool kSmem>
+void launch_unpermute(const uint32_t *bits, const int *rank_of_pos, int mr, int n, int nwords, uint32_t *jbits,
+                      uint32_t *gcount, size_t smem, cudaStream_t st) {
+    FB_CUDA(cudaFuncSetAttribute(unpermute_kernel<R, kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)std::max<size_t>(smem, 1024)));
+    unpermute_kernel<R, kSmem><<<(unsigned)ceil_div(mr, R), kFillThreads, smem, st>>>(bits, rank_of_pos, mr, n,
+                                                                                       nwords, jbits, gcount);
+}
+
+// words of J-order scratch launch_fill needs for mr rows: the words themselves + the per-group counts
+inline size_t fill_scratch_words(size_t mr, int nwords) {
+    return mr * (size_t)std::max(nwords, 1) + mr * (size_t)ceil_div(std::max(nwords, 1), 32);
+}
+
 template <class T> void launch_fill(fluxb200_mesh *M, size_t row0, size_t mr, const uint32_t *bits,
                                     const int64_t *indptr_local, int64_t out_base, T *data, void *indices,
-                                    int index_width, cudaStream_t st) {
+                                    int index_width, uint32_t *jbits, cudaStream_t st) {
+    const int nwords = M->nwords, n = (int)M->n;
+    const size_t row_bytes = sizeof(uint32_t) * (size_t)nwords;
+    uint32_t *gcount = jbits + mr * (size_t)nwords;
+    // rows per CTA: four CTAs per SM when >= 2 rows fit in a quarter of the shared memory, else fewer CTAs
+    const size_t budget_q = (size_t)M->max_smem_optin / 4 - 1024, budget_full = (size_t)M->max_smem_optin - 1024;
+    size_t R = budget_q / row_bytes;
+    if (R < 2) R = (budget_full / 2) / row_bytes;
+    if (R < 2) R = budget_full / row_bytes;
+    if (M->fill_rows_opt > 0) R = std::min<size_t>(budget_full / row_bytes, (size_t)M->fill_rows_opt); // A/B and tests
+    if (M->fill_rows_opt < 0) R = 0;
+    const int *rank = M->rank_of_pos.as<int>();
+    if (R >= 8) launch_unpermute<8, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 8 * row_bytes, st);
+    else if (R >= 4) launch_unpermute<4, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 4 * row_bytes, st);
+    else if (R >= 2) launch_unpermute<2, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 2 * row_bytes, st);
+    else if (R == 1) launch_unpermute<1, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, row_bytes, st);
+    else launch_unpermute<1, false>(bits, rank, (int)mr, n, nwords, jbits, gcount, 0, st);
+    FB_CUDA(cudaGetLastError());
     FillArgs<T> A;
     A.faceP = M->faceP.as<Real4<T>>();
     A.faceN = M->faceN.as<Real4<T>>();
     A.rows = M->rows.as<int>() + row0;
     A.cols = M->cols.as<int>();
-    A.rank_of_pos = M->rank_of_pos.as<int>();
     A.m = (int)mr;
     A.n = (int)M->n;
-    A.nwords = M->nwords;
-    A.bits = bits;
+    A.nwords = nwords;
+    A.jbits = jbits;
+    A.gcount = gcount;
     A.indptr = indptr_local;
     A.out_base = out_base;
     A.data = data;
     A.indices = indices;
     A.index_width = index_width;
-    size_t smem = sizeof(uint32_t) * (size_t)M->nwords;
-    A.bits_in_smem = (int)smem + 1024 <= M->max_smem_optin;
-    if (!A.bits_in_smem) smem = 0;
-    FB_CUDA(cudaFuncSetAttribute(fill_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)std::max<size_t>(smem, 1024)));
-    fill_kernel<T><<<(unsigned)mr, kFillThreads, smem, st>>>(A);
+    // enough CTAs (8 rows x one column segment each) to fill the machine about four times over
+    const int64_t row_blocks = ceil_div((int64_t)mr, kFillWarps), ngroups = ceil_div(nwords, 32);
+    const int64_t segs = std::max<int64_t>(1, std::min<int64_t>(ngroups, ceil_div(4 * (int64_t)M->num_sms, row_blocks)));
+    FB_CUDA(cudaFuncSetAttribute(emit_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)emit_smem_bytes<T>()));
+    emit_kernel<T><<<dim3((unsigned)row_blocks, (unsigned)segs), kFillThreads, emit_smem_bytes<T>(), st>>>(A);
     FB_CUDA(cudaGetLastError());
 }
+constexpr int kFillLaunches = 2; // kernels per launch_fill
 
 // ---- two-phase API: count (all rows, bits kept on the device), then fill ---------
 template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
@@ -450,6 +502,7 @@ template <class T> void ff_count(fluxb200_mesh *M, const int64_t *I, size_t m, c
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_trace, M->ev[1], M->ev[2]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_scan, M->ev[2], M->ev[3]));
     M->stats.kernel_launches = launches;
+    M->stats.d2h_bytes = (int64_t)(sizeof(int64_t) + sizeof(tested) + (row_counts ? sizeof(int64_t) * m : 0));
     check_error_flag(M);
     M->have_count = true;
 }
@@ -478,9 +531,15 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_CUDA(cudaEventRecord(M->ev[0], st));
     int launches = 0;
     if (m && n && nnz) {
-        launch_fill<T>(M, 0, m, M->bits.as<uint32_t>(), M->indptr.as<int64_t>(), 0, d_data, d_indices,
-                       index_width, st);
-        ++launches;
+        // pieces of <= 4096 rows bound the J-order scratch (the pieces run back to back on one stream)
+        const size_t piece = std::min<size_t>(m, 4096);
+        M->jbits.reserve(sizeof(uint32_t) * fill_scratch_words(piece, M->nwords));
+        for (size_t r0 = 0; r0 < m; r0 += piece) {
+            const size_t mr = std::min(piece, m - r0);
+            launch_fill<T>(M, r0, mr, M->bits.as<uint32_t>() + r0 * (size_t)M->nwords, M->indptr.as<int64_t>() + r0,
+                           0, d_data, d_indices, index_width, M->jbits.as<uint32_t>(), st);
+            launches += kFillLaunches;
+        }
     }
     void *d_indptr = M->indptr.p;
     if (index_width == 4) {
@@ -505,12 +564,15 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_fill, M->ev[0], M->ev[1]));
     FB_CUDA(cudaEventElapsedTime(&M->stats.ms_d2h, M->ev[1], M->ev[2]));
     M->stats.kernel_launches += launches;
+    if (destination == 0)
+        M->stats.d2h_bytes += (int64_t)((size_t)index_width * (m + 1) + ((size_t)index_width + sizeof(T)) * (size_t)nnz);
     M->out_index_width = destination == 2 ? index_width : 0;
 }
 
-// ---- streaming assembly: row sub-slabs pipelined over two streams ------------------
+// ---- streaming assembly: row sub-slabs pipelined over three streams ----------------
 // compute stream: trace(k) -> counts(k) -> local indptr(k) -> nnz(k), counts(k) to pinned host
-// copy stream   : fill(k) -> D2H(k)   (runs under trace(k+1); bits / staging double-buffered)
+// fill stream   : fill(k)             (submitted before trace(k+1), see below)
+// copy-out      : D2H(k)              (runs under trace(k+1); bits / staging triple-buffered)
 // Returns false when `capacity` entries do not suffice (stats.nnz = entries needed).
 template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
                                     double eps, int index_width, int destination, void *indptr,
@@ -518,7 +580,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
     FB_REQUIRE(destination == 0 || destination == 2, "destination must be 0 (host) or 2 (library device buffers)");
     if (index_width == 4) FB_REQUIRE(n < (1ull << 31), "int32 indices cannot hold this many columns");
-    cudaStream_t s0 = M->stream, s1 = M->copy_stream;
+    cudaStream_t s0 = M->stream, s1 = M->copy_stream, s2 = M->d2h_stream;
     FB_CUDA(cudaEventRecord(M->ev[0], s0));
     int launches = prepare_call<T>(M, I, m, J, n, eps);
     FB_CUDA(cudaEventRecord(M->ev[1], s0));
@@ -531,12 +593,12 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     std::vector<size_t> bounds{0};
     {
         size_t pos = 0;
-        const size_t min_piece = std::max<size_t>(32, sub / 8);
+        const size_t min_piece = std::min(sub, std::max<size_t>(32, sub / 4)); // never above the slot size
         while (pos < m) {
             const size_t rem = m - pos;
             size_t piece = sub;
             if (destination == 0 && rem <= 2 * sub) piece = std::max(min_piece, (rem + 1) / 2);
-            piece = std::min(piece, rem);
+            piece = std::min(std::min(piece, sub), rem);
             pos += piece;
             bounds.push_back(pos);
         }
@@ -548,6 +610,33 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         M->scounts[b].reserve(sizeof(uint32_t) * sub);
         M->scounts64[b].reserve(sizeof(int64_t) * sub);
         M->sindptr[b].reserve(sizeof(int64_t) * (sub + 1));
+        M->sjbits[b].reserve(sizeof(uint32_t) * fill_scratch_words(sub, M->nwords));
+    }
+    // host output: the column indices travel as J-order visibility words (n/8 bytes per row instead
+    // of 4 or 8 bytes per entry) and host threads expand them while the next sub-slabs are traced
+    const bool expand = destination == 0 && M->host_expand_opt != 0 && n > 0;
+    const size_t slot_words = sub * (size_t)std::max(M->nwords, 1);
+    std::vector<std::unique_ptr<ExpandTask>> tasks(expand ? nsub : 0);
+    struct TaskGuard { // no worker may outlive the buffers it writes to, whatever path leaves this frame
+        fluxb200_mesh *M;
+        std::vector<std::unique_ptr<ExpandTask>> &tasks;
+        ~TaskGuard() {
+            cudaStreamSynchronize(M->copy_stream);
+            cudaStreamSynchronize(M->d2h_stream); // every callback that will ever fire has fired
+            for (auto &t : tasks)
+                if (t && t->queued.load()) M->expander.wait(t.get());
+        }
+    } task_guard{M, tasks};
+    if (expand) {
+        int nthreads = M->host_threads_opt;
+        if (nthreads <= 0) { // share the host cores with the other ranks of a torchrun job
+            const char *lws = getenv("LOCAL_WORLD_SIZE");
+            const int ranks = std::max(1, lws ? atoi(lws) : 1);
+            const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+            nthreads = std::min(8, std::max(1, hw / (2 * ranks)));
+        }
+        M->expander.start(nthreads);
+        M->h_jbits.reserve(sizeof(uint32_t) * slot_words * fluxb200_mesh::kHostSlots);
     }
     M->h_nnz.reserve(sizeof(int64_t) * std::max<size_t>(nsub, 1));
     M->h_counts.reserve(sizeof(uint32_t) * std::max<size_t>(m, 1));
@@ -556,6 +645,17 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         FB_CUDA(cudaEventCreate(&e));
         M->sub_events.push_back(e);
     }
+    // FLUXB200_TIMELINE=<file>: per-sub-slab device timestamps of trace / fill / copy-out (diagnostic)
+    const char *tl_path = getenv("FLUXB200_TIMELINE");
+    std::vector<double> tl_host(tl_path ? 3 * nsub : 0);
+    const auto tl_clock0 = std::chrono::steady_clock::now();
+    auto tl_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl_clock0).count(); };
+    if (tl_path)
+        while (M->tl_events.size() < 4 * nsub) {
+            cudaEvent_t e;
+            FB_CUDA(cudaEventCreate(&e));
+            M->tl_events.push_back(e);
+        }
     if (destination == 2) {
         if (capacity <= 0)
             capacity = M->dev_capacity_hint > 0
@@ -565,9 +665,11 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         M->out_data.reserve(sizeof(T) * (size_t)capacity);
         M->out_indices.reserve((size_t)index_width * (size_t)capacity);
     }
-    int64_t *h_nnz = M->h_nnz.as<int64_t>();
-    uint32_t *h_counts = M->h_counts.as<uint32_t>();
-    int64_t total = 0;
+    int64_t *h_nnz = M->h_nnz.as<int64_t>(), *h_nnz_dev = nullptr;
+    uint32_t *h_counts = M->h_counts.as<uint32_t>(), *h_counts_dev = nullptr;
+    FB_CUDA(cudaHostGetDevicePointer((void **)&h_nnz_dev, h_nnz, 0));
+    FB_CUDA(cudaHostGetDevicePointer((void **)&h_counts_dev, h_counts, 0));
+    int64_t total = 0, d2h_bytes = 0;
     bool overflow = false;
     float ms_fill = 0.f;
 
@@ -577,6 +679,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         if (k >= (size_t)fluxb200_mesh::kSlots)
             FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0)); // fill(k - kSlots) is done with slot b
         FB_CUDA(cudaMemsetAsync(M->scounts[b].p, 0, sizeof(uint32_t) * mr, s0));
+        if (tl_path) tl_host[3 * k] = tl_now();
         FB_CUDA(cudaEventRecord(M->sub_events[3 * k], s0));
         if (n) launch_trace<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->scounts[b].as<uint32_t>(), s0);
         FB_CUDA(cudaEventRecord(M->sub_events[3 * k + 1], s0));
@@ -584,16 +687,18 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
                                                                           M->scounts64[b].as<int64_t>());
         scan_exclusive<int64_t, int64_t>(M->scounts64[b].as<int64_t>(), M->sindptr[b].as<int64_t>(), (int64_t)mr,
                                          M->sindptr[b].as<int64_t>() + mr, s0);
-        FB_CUDA(cudaMemcpyAsync(h_nnz + k, M->sindptr[b].as<int64_t>() + mr, sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, s0));
-        FB_CUDA(cudaMemcpyAsync(h_counts + row0, M->scounts[b].p, sizeof(uint32_t) * mr, cudaMemcpyDeviceToHost, s0));
+        publish_counts_kernel<<<blocks_for((int64_t)mr, 256), 256, 0, s0>>>(
+            M->scounts[b].as<uint32_t>(), (int)mr, M->sindptr[b].as<int64_t>() + mr, h_counts_dev + row0, h_nnz_dev + k);
+        FB_CUDA(cudaGetLastError());
         FB_CUDA(cudaEventRecord(M->sub_events[3 * k + 2], s0));
-        launches += (n ? 1 : 0) + 2;
+        d2h_bytes += (int64_t)(sizeof(int64_t) + sizeof(uint32_t) * mr);
+        launches += (n ? 1 : 0) + 3;
     };
     auto finish = [&](size_t k) {
         const int b = (int)(k % fluxb200_mesh::kSlots);
         const size_t row0 = bounds[k], mr = bounds[k + 1] - row0;
         FB_CUDA(cudaEventSynchronize(M->sub_events[3 * k + 2]));
+        if (tl_path) tl_host[3 * k + 1] = tl_now();
         const int64_t nnz_k = h_nnz[k], off = total;
         total += nnz_k;
         if (index_width == 4 && total >= (1ll << 31)) throw CudaError{"int32 indices cannot hold this matrix"};
@@ -610,24 +715,69 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
                 base = off;
             } else {
                 M->stage_data[b].reserve(sizeof(T) * (size_t)nnz_k);
-                M->stage_idx[b].reserve((size_t)index_width * (size_t)nnz_k);
+                if (!expand) M->stage_idx[b].reserve((size_t)index_width * (size_t)nnz_k);
                 d_data = M->stage_data[b].as<T>();
                 d_idx = M->stage_idx[b].p;
                 base = 0;
             }
+            if (destination == 0 && k >= (size_t)fluxb200_mesh::kSlots)
+                FB_CUDA(cudaStreamWaitEvent(s1, M->d2h_done[b], 0)); // the slot's staging has left the device
+            if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k], s1));
             launch_fill<T>(M, row0, mr, M->sbits[b].as<uint32_t>(), M->sindptr[b].as<int64_t>(), base, d_data,
-                           d_idx, index_width, s1);
-            ++launches;
+                           expand ? nullptr : d_idx, index_width, M->sjbits[b].as<uint32_t>(), s1);
+            if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k + 1], s1));
+            launches += kFillLaunches;
             FB_CUDA(cudaEventRecord(M->slot_free[b], s1)); // bits / indptr of the slot are consumed
             slot_recorded = true;
             if (destination == 0) {
+                FB_CUDA(cudaStreamWaitEvent(s2, M->slot_free[b], 0));
+                if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k + 2], s2));
                 FB_CUDA(cudaMemcpyAsync((char *)data + sizeof(T) * (size_t)off, d_data, sizeof(T) * (size_t)nnz_k,
-                                        cudaMemcpyDeviceToHost, s1));
-                FB_CUDA(cudaMemcpyAsync((char *)indices + (size_t)index_width * (size_t)off, d_idx,
-                                        (size_t)index_width * (size_t)nnz_k, cudaMemcpyDeviceToHost, s1));
+                                        cudaMemcpyDeviceToHost, s2));
+                d2h_bytes += (int64_t)(sizeof(T) * (size_t)nnz_k);
+                d2h_bytes += expand ? (int64_t)(sizeof(uint32_t) * mr * (size_t)M->nwords)
+                                    : (int64_t)((size_t)index_width * (size_t)nnz_k);
+                if (expand) {
+                    // the host slot is free once the sub-slab that used it last has been expanded
+                    if (k >= (size_t)fluxb200_mesh::kHostSlots && tasks[k - fluxb200_mesh::kHostSlots])
+                        M->expander.wait(tasks[k - fluxb200_mesh::kHostSlots].get());
+                    uint32_t *h_words = M->h_jbits.as<uint32_t>() + (k % fluxb200_mesh::kHostSlots) * slot_words;
+                    FB_CUDA(cudaMemcpyAsync(h_words, M->sjbits[b].p, sizeof(uint32_t) * mr * (size_t)M->nwords,
+                                            cudaMemcpyDeviceToHost, s2));
+                    tasks[k].reset(new ExpandTask());
+                    ExpandTask *t = tasks[k].get();
+                    t->words = h_words;
+                    t->nwords = M->nwords;
+                    t->mr = mr;
+                    t->offs.resize(mr + 1);
+                    t->offs[0] = off;
+                    for (size_t r = 0; r < mr; ++r) t->offs[r + 1] = t->offs[r] + (int64_t)h_counts[row0 + r];
+                    t->indices = indices;
+                    t->index_width = index_width;
+                    t->pieces = (int)std::max<size_t>(1, std::min<size_t>(mr, 2 * (size_t)M->expander.threads()));
+                    t->pending.store(t->pieces);
+                    t->owner = &M->expander;
+                    FB_CUDA(cudaLaunchHostFunc(s2, [](void *arg) {
+                        ExpandTask *t = reinterpret_cast<ExpandTask *>(arg);
+                        t->queued.store(1);
+                        t->owner->submit(t);
+                    }, t));
+                } else {
+                    FB_CUDA(cudaMemcpyAsync((char *)indices + (size_t)index_width * (size_t)off, d_idx,
+                                            (size_t)index_width * (size_t)nnz_k, cudaMemcpyDeviceToHost, s2));
+                }
+                if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k + 3], s2));
+                FB_CUDA(cudaEventRecord(M->d2h_done[b], s2));
             }
         }
-        if (!slot_recorded) FB_CUDA(cudaEventRecord(M->slot_free[b], s1));
+        if (tl_path) tl_host[3 * k + 2] = tl_now();
+        if (!slot_recorded) {
+            FB_CUDA(cudaEventRecord(M->slot_free[b], s1));
+            if (destination == 0) { // keep d2h_done[b] a valid "slot is free" marker for sub-slab k + kSlots
+                FB_CUDA(cudaStreamWaitEvent(s2, M->slot_free[b], 0));
+                FB_CUDA(cudaEventRecord(M->d2h_done[b], s2));
+            }
+        }
     };
 
     FB_CUDA(cudaEventRecord(M->ev[4], s1));
@@ -639,12 +789,38 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         enqueue_trace(k);
         finish(k);
     }
+    FB_CUDA(cudaEventRecord(M->slot_free[0], s2)); // (reused as a plain marker) copy-out done -> span end on s1
+    FB_CUDA(cudaStreamWaitEvent(s1, M->slot_free[0], 0));
     FB_CUDA(cudaEventRecord(M->ev[5], s1));
     FB_CUDA(cudaEventRecord(M->ev[2], s0));
     unsigned long long tested = 0;
     FB_CUDA(cudaMemcpyAsync(&tested, M->tested.p, sizeof(tested), cudaMemcpyDeviceToHost, s0));
     FB_CUDA(cudaStreamSynchronize(s0));
     FB_CUDA(cudaStreamSynchronize(s1));
+    FB_CUDA(cudaStreamSynchronize(s2));
+    for (auto &t : tasks) {
+        if (!t) continue;
+        FB_REQUIRE(t->queued.load(), "internal: a copy-out callback did not run");
+        M->expander.wait(t.get());
+        FB_REQUIRE(t->mismatch.load() == 0, "internal: visibility words and row counts disagree");
+    }
+    if (tl_path && destination == 0 && !overflow) {
+        if (FILE *f = fopen(tl_path, "w")) {
+            fprintf(f, "k,rows,host_submit_trace,host_trace_done,host_fill_submitted,trace0,trace1,scan1,fill0,fill1,d2h0,d2h1\n");
+            auto rel = [&](cudaEvent_t e) {
+                float ms = -1.f;
+                if (cudaEventElapsedTime(&ms, M->ev[0], e) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+                return ms;
+            };
+            for (size_t k = 0; k < nsub; ++k)
+                fprintf(f, "%zu,%zu,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", k, bounds[k + 1] - bounds[k],
+                        tl_host[3 * k], tl_host[3 * k + 1], tl_host[3 * k + 2], rel(M->sub_events[3 * k]),
+                        rel(M->sub_events[3 * k + 1]), rel(M->sub_events[3 * k + 2]), rel(M->tl_events[4 * k]),
+                        rel(M->tl_events[4 * k + 1]), rel(M->tl_events[4 * k + 2]), rel(M->tl_events[4 * k + 3]));
+            fprintf(f, "# host total %.3f ms\n", tl_now());
+            fclose(f);
+        }
+    }
     // leave the handle's main stream ordered after the copy stream
     M->nnz = total;
     M->stats.nnz = total;
@@ -664,6 +840,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     M->stats.ms_d2h = 0.f;
     M->stats.trace_launches = (int)nsub;
     M->stats.kernel_launches = launches;
+    M->stats.d2h_bytes = d2h_bytes + (int64_t)sizeof(tested);
     if (row_counts)
         for (size_t r = 0; r < m; ++r) row_counts[r] = (int64_t)h_counts[r];
     check_error_flag(M);
@@ -780,7 +957,9 @@ int fluxb200_mesh_create(const void *V, size_t nv, const int64_t *F, size_t nf, 
         FB_CUDA(cudaStreamCreateWithPriority(&M->stream, cudaStreamNonBlocking, prio_lo));
         // fill + copies run under the persistent trace kernel: let them win free CTA slots
         FB_CUDA(cudaStreamCreateWithPriority(&M->copy_stream, cudaStreamNonBlocking, prio_hi));
+        FB_CUDA(cudaStreamCreateWithPriority(&M->d2h_stream, cudaStreamNonBlocking, prio_hi));
         for (auto &e : M->slot_free) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : M->d2h_done) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : M->ev) FB_CUDA(cudaEventCreate(&e));
         FB_CUDA(cudaDeviceGetAttribute(&M->num_sms, cudaDevAttrMultiProcessorCount, device));
         FB_CUDA(cudaDeviceGetAttribute(&M->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -818,16 +997,20 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
                           &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->node_range, &M->rows,
                           &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
-                          &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout};
+                          &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout, &M->jbits};
         for (DevBuf *b : bufs) b->release();
         for (int k = 0; k < fluxb200_mesh::kSlots; ++k) {
             M->sbits[k].release(); M->scounts[k].release(); M->scounts64[k].release(); M->sindptr[k].release();
             M->stage_data[k].release(); M->stage_idx[k].release();
+            M->sjbits[k].release();
             if (M->slot_free[k]) cudaEventDestroy(M->slot_free[k]);
+            if (M->d2h_done[k]) cudaEventDestroy(M->d2h_done[k]);
         }
-        M->h_nnz.release(); M->h_counts.release();
+        M->h_nnz.release(); M->h_counts.release(); M->h_jbits.release();
         for (auto &e : M->sub_events) cudaEventDestroy(e);
+        for (auto &e : M->tl_events) cudaEventDestroy(e);
         if (M->copy_stream) { cudaStreamSynchronize(M->copy_stream); cudaStreamDestroy(M->copy_stream); }
+        if (M->d2h_stream) { cudaStreamSynchronize(M->d2h_stream); cudaStreamDestroy(M->d2h_stream); }
         M->sorter.release();
         for (auto &e : M->ev)
             if (e) cudaEventDestroy(e);
@@ -1270,6 +1453,15 @@ int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *st
     });
 }
 
+int fluxb200_expand_words(const uint32_t *words, size_t nwords, int index_width, void *out, int64_t *count) {
+    return guarded([&] {
+        FB_REQUIRE((words || !nwords) && out && count, "NULL argument");
+        FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
+        FB_REQUIRE(nwords < (1ull << 26), "too many words");
+        *count = expand_words(words, (int)nwords, index_width, out);
+    });
+}
+
 int fluxb200_mesh_stream(fluxb200_mesh *M, void **stream) {
     return guarded([&] {
         FB_REQUIRE(M && stream, "NULL argument");
@@ -1297,6 +1489,14 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->top_nodes_opt = (int)value;
             M->have_count = false;
             bvh_build(M);
+        } else if (s == "host_expand") {
+            M->host_expand_opt = value ? 1 : 0;
+        } else if (s == "host_threads") {
+            FB_REQUIRE(value >= 0 && value <= 64, "host_threads out of range");
+            M->host_threads_opt = (int)value;
+        } else if (s == "fill_rows") {
+            FB_REQUIRE(value >= -1 && value <= 8, "fill_rows out of range");
+            M->fill_rows_opt = (int)value;
         } else if (s == "sub_rows") {
             FB_REQUIRE(value >= 1 && value <= (1 << 20), "sub_rows out of range");
             M->sub_rows_opt = (int)value;

@@ -1,0 +1,134 @@
+// host_expand.cpp -- host side of the CSR copy-out: column indices from visibility words.
+//
+// The column indices of a CSR row of the form-factor matrix are exactly the
+// positions of the set bits of that row's visibility words (original column
+// order, form_factors.py:52, 69).  fluxb200_ff_assemble therefore ships the
+// words (n/8 bytes per row) over PCIe instead of the int32 positions (4 bytes
+// per stored entry) and a few host threads write the positions while the next
+// sub-slab is traced.  This is a transport encoding, not a compute fallback:
+// the words come from the GPU kernels.
+#include "host_expand.h"
+#include <stdlib.h>
+#include <string.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace fluxb200 {
+
+namespace {
+
+template <class Index> int64_t expand_scalar(const uint32_t *words, int nwords, Index *out) {
+    Index *dst = out;
+    for (int k = 0; k < nwords; ++k) {
+        uint32_t w = words[k];
+        const Index base = (Index)k * 32;
+        while (w) {
+            *dst++ = base + (Index)__builtin_ctz(w);
+            w &= w - 1;
+        }
+    }
+    return (int64_t)(dst - out);
+}
+
+#if defined(__x86_64__)
+// 16 column positions per step: compress the lane ids selected by 16 mask bits, masked store
+__attribute__((target("avx512f"))) int64_t expand_avx512(const uint32_t *words, int nwords, int32_t *out) {
+    int32_t *dst = out;
+    const __m512i lanes = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    for (int k = 0; k < nwords; ++k) {
+        const uint32_t w = words[k];
+        if (!w) continue;
+        const __m512i base = _mm512_add_epi32(lanes, _mm512_set1_epi32(k * 32));
+        const __mmask16 lo = (__mmask16)(w & 0xffffu), hi = (__mmask16)(w >> 16);
+        const int clo = __builtin_popcount(lo), chi = __builtin_popcount(hi);
+        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << clo) - 1u), _mm512_maskz_compress_epi32(lo, base));
+        dst += clo;
+        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << chi) - 1u),
+                                 _mm512_maskz_compress_epi32(hi, _mm512_add_epi32(base, _mm512_set1_epi32(16))));
+        dst += chi;
+    }
+    return (int64_t)(dst - out);
+}
+#endif
+
+bool have_avx512() {
+#if defined(__x86_64__)
+    // FLUXB200_NO_AVX512 forces the portable loop (tests cover both)
+    static const bool v = __builtin_cpu_supports("avx512f") && !getenv("FLUXB200_NO_AVX512");
+    return v;
+#else
+    return false;
+#endif
+}
+
+} // namespace
+
+int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out) {
+    if (index_width == 8) return expand_scalar<int64_t>(words, nwords, reinterpret_cast<int64_t *>(out));
+#if defined(__x86_64__)
+    if (have_avx512()) return expand_avx512(words, nwords, reinterpret_cast<int32_t *>(out));
+#endif
+    return expand_scalar<int32_t>(words, nwords, reinterpret_cast<int32_t *>(out));
+}
+
+// ---- worker pool -------------------------------------------------------------------
+HostExpander::~HostExpander() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto &t : workers_) t.join();
+}
+
+void HostExpander::start(int nthreads) {
+    std::lock_guard<std::mutex> lk(mu_);
+    while ((int)workers_.size() < nthreads) workers_.emplace_back([this] { run(); });
+}
+
+void HostExpander::submit(ExpandTask *t) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (int p = 0; p < t->pieces; ++p) queue_.emplace_back(t, p);
+    }
+    cv_work_.notify_all();
+}
+
+void HostExpander::wait(ExpandTask *t) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [t] { return t->pending.load() == 0; });
+}
+
+void HostExpander::run() {
+    for (;;) {
+        std::pair<ExpandTask *, int> item;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_work_.wait(lk, [this] { return stop_ || !queue_.empty(); });
+            if (queue_.empty()) return; // stop_
+            item = queue_.front();
+            queue_.pop_front();
+        }
+        ExpandTask *t = item.first;
+        const size_t r0 = t->mr * (size_t)item.second / (size_t)t->pieces;
+        const size_t r1 = t->mr * (size_t)(item.second + 1) / (size_t)t->pieces;
+        for (size_t r = r0; r < r1; ++r) {
+            const uint32_t *w = t->words + r * (size_t)t->nwords;
+            int64_t bits = 0;
+            for (int k = 0; k < t->nwords; ++k) bits += __builtin_popcount(w[k]);
+            if (bits != t->offs[r + 1] - t->offs[r]) { // never write outside the row's range
+                t->mismatch.store(1);
+                continue;
+            }
+            char *dst = reinterpret_cast<char *>(t->indices) + (size_t)t->index_width * (size_t)t->offs[r];
+            expand_words(w, t->nwords, t->index_width, dst);
+        }
+        if (t->pending.fetch_sub(1) == 1) {
+            std::lock_guard<std::mutex> lk(mu_); // pairs with the predicate check in wait()
+            cv_done_.notify_all();
+        }
+    }
+}
+
+} // namespace fluxb200

@@ -200,6 +200,17 @@ __device__ __forceinline__ bool leaf_occludes(const BvhView &bvh, const Ray &r, 
     return t < tlimit || __float_as_int(p0.w) > target_face;
 }
 
+// out-of-line copy for the rare lane whose deferred-candidate list is full (K4)
+__device__ __noinline__ bool leaf_occludes_cold(const float4 *tri, Ray r, float tlimit, int leaf,
+                                                int target_face) {
+    const float4 p0 = __ldg(tri + 3 * (size_t)leaf);
+    const float4 p1 = __ldg(tri + 3 * (size_t)leaf + 1);
+    const float4 p2 = __ldg(tri + 3 * (size_t)leaf + 2);
+    float t;
+    if (!pluecker_hit(r, 0.0f, tlimit, p0, p1, p2, t)) return false;
+    return t < tlimit || __float_as_int(p0.w) > target_face;
+}
+
 // Generic any-hit traversal with immediate leaf tests (query kernels).
 // With tlimit = t of the target triangle this is "closest hit != target" of the
 // oracle's index-ordered closest-hit definition.  tlimit = +inf, target_leaf =

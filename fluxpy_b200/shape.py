@@ -267,7 +267,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
     _fill_ratio = 0.55
     overflow_retries = 0
 
-    def _ff_assemble_host(self, I, J, eps, want_row_counts=False):
+    def _ff_assemble_host(self, I, J, eps, want_row_counts=False, index_dtype=None):
         """Streaming assembly (``fluxb200_ff_assemble``) into page-locked host
         buffers from the arena; returns zero-copy NumPy views trimmed to nnz.
         Falls back to one retry with the exact size when the estimate was short."""
@@ -282,7 +282,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         esz = np.dtype(self.dtype).itemsize
         cap = int(min(m*n, max(1024, self._fill_ratio*1.2*m*n + 4096)))
         while True:
-            idt = np.int32 if max(cap, n, m + 1) < 2**31 else np.int64
+            idt = index_dtype or (np.int32 if max(cap, n, m + 1) < 2**31 else np.int64)
             isz = np.dtype(idt).itemsize
             off_idx = -(-(cap*esz)//256)*256
             off_ptr = off_idx + -(-(cap*isz)//256)*256

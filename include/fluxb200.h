@@ -34,7 +34,7 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 4
+#define FLUXB200_ABI_VERSION 5
 
 #define FLUXB200_OK 0
 #define FLUXB200_ERROR 1
@@ -55,6 +55,8 @@ typedef struct fluxb200_ff_stats {
     float ms_d2h;         /* device -> host copies of the CSR arrays */
     int32_t trace_launches;
     int32_t kernel_launches; /* all kernels launched by the last count+fill */
+    int64_t h2d_bytes;    /* bytes copied host -> device by the call (index sets) */
+    int64_t d2h_bytes;    /* bytes copied device -> host by the call (CSR arrays or visibility words, counts) */
 } fluxb200_ff_stats;
 
 typedef struct fluxb200_bvh_info {
@@ -209,13 +211,24 @@ int fluxb200_visibility_bruteforce(fluxb200_mesh *mesh, const int64_t *I, size_t
  * be NULL for an equal split. */
 int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *starts);
 
+/* Host helper of the copy-out of fluxb200_ff_assemble (destination 0): the column
+ * indices of a CSR row (form_factors.py:52, 69) are the positions of the set bits
+ * of the row's visibility words in the caller's column order; the words cross
+ * PCIe, this writes the positions (ascending; int32 or int64) and their number.
+ * `out` must hold popcount(words) entries.  Exported for the host-logic tests. */
+int fluxb200_expand_words(const uint32_t *words, size_t nwords, int index_width, void *out,
+                          int64_t *count);
+
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, so a
  * caller can bracket calls with its own events. */
 int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
 /* Tunables: "top_nodes" (BVH nodes staged in shared memory), "slab_limit"
  * (largest subtree, in faces, that gets a fitted slab), "blocks_per_sm" (persistent CTAs per SM of
  * the trace kernel), "shaft_filter" (0 disables the per-unit record filter: A/B checks),
- * "sub_rows" (rows per sub-slab of fluxb200_ff_assemble). */
+ * "sub_rows" (rows per sub-slab of fluxb200_ff_assemble), "fill_rows" (rows per CTA of the
+ * CSR fill's un-permute kernel: 0 = as many as fit in shared memory, -1 = no shared memory),
+ * "host_expand" (1: fluxb200_ff_assemble ships visibility words to the host and host threads
+ * write the column indices; 0: the indices themselves are copied), "host_threads" (0 = automatic). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 
 #ifdef __cplusplus

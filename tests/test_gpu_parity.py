@@ -297,6 +297,27 @@ def test_slab_properties_at_full_size(mods):
     assert same_csr(gf(sm, samp), mods['oracle'].get_form_factor_matrix(om, samp))
 
 
+def test_fill_kernel_variants_agree(mods):
+    """K6a stages 1, 2, 4 or 8 rows per CTA in shared memory, or none (rows too
+    long for it): every variant writes the same CSR as the oracle, for an
+    unsorted, non-contiguous J whose length is not a multiple of 32 or 1024."""
+    V, F = mods['meshes'].gaussian_crater(40, 2, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N)
+    om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    rng = np.random.default_rng(11)
+    nf = sm.num_faces
+    I = rng.permutation(nf)[:37]
+    J = rng.permutation(nf)[:2531]
+    ref = mods['oracle'].get_form_factor_matrix(om, I, J)
+    for rows_per_cta in (0, 1, 2, 4, 8, -1):
+        sm.set_option('fill_rows', rows_per_cta)
+        assert same_csr(mods['ff'].get_form_factor_matrix(sm, I, J), ref), rows_per_cta
+        m, n, counts, st = sm._ff_count(I, J, 1e-5)
+        ip, ix, dv, _ = sm._ff_fill_host(m, int(st.nnz), np.int64)
+        assert np.array_equal(ix, ref.indices) and np.array_equal(dv, ref.data), rows_per_cta
+
+
 def test_streaming_and_two_phase_paths_agree(mods):
     """fluxb200_ff_assemble (sub-slab pipeline, pinned arena, overflow retry,
     device-resident CSR) == fluxb200_ff_count + fluxb200_ff_fill, bit for bit."""
@@ -320,6 +341,15 @@ def test_streaming_and_two_phase_paths_agree(mods):
         assert same_csr(FF, ref)
         m2, n2, ip2, ix2, dv2, c2, st2 = sm._ff_assemble_host(I, J, 1e-5, want_row_counts=True)
         assert np.array_equal(c2, counts) and st2.nnz == st.nnz and st2.pairs_tested == st.pairs_tested
+        # copy-out: column indices expanded on the host from the visibility words (default) ==
+        # indices copied from the device, int32 and int64
+        for expand in (0, 1):
+            sm.set_option('host_expand', expand)
+            for idt in (np.int32, np.int64):
+                _, _, ip3, ix3, dv3, _, _ = sm._ff_assemble_host(I, J, 1e-5, index_dtype=idt)
+                assert ix3.dtype == idt and np.array_equal(ix3, ix) and np.array_equal(ip3, ip)
+                assert np.array_equal(dv3, dv)
+        sm.set_option('host_threads', 1 + sub % 3)
         # int64 index path of the two-phase API
         ip8, ix8, dv8, _ = (lambda r: r)(sm._ff_count(I, J, 1e-5)) and sm._ff_fill_host(m, int(st.nnz), np.int64)
         assert np.array_equal(ix8, ix) and ix8.dtype == np.int64 and np.array_equal(dv8, dv)

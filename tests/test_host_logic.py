@@ -28,7 +28,7 @@ def test_no_oracle_in_product_path():
     pkg = os.path.join(ROOT, 'fluxpy_b200')
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith(('.py', '.cu', '.cuh', '.h')) or f == 'Makefile':
+            if f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')) or f == 'Makefile':
                 txt = open(os.path.join(dirpath, f)).read()
                 for needle in ('import oracle', 'from oracle', 'ff_oracle', 'oracle/', 'oracle.'):
                     assert needle not in txt, (f, needle)
@@ -53,6 +53,44 @@ def test_missing_device_fails_loudly():
         dtype = np.dtype(np.float32)
     with pytest.raises(RuntimeError):
         get_form_factor_matrix(Fake())
+
+
+def _expand(words, width):
+    from fluxpy_b200 import _lib
+    words = np.ascontiguousarray(words, np.uint32)
+    out = np.full(int(np.unpackbits(words.view(np.uint8)).sum()) + 4, -7, np.int32 if width == 4 else np.int64)
+    cnt = ctypes.c_int64(-1)
+    _lib.check(_lib.lib().fluxb200_expand_words(_lib.ptr(words), len(words), width, _lib.ptr(out),
+                                                ctypes.byref(cnt)))
+    assert (out[cnt.value:] == -7).all()          # nothing written past the row
+    return out[:cnt.value]
+
+
+def test_expand_words_matches_numpy():
+    """Host half of the copy-out: set-bit positions of the visibility words ==
+    np.flatnonzero of the unpacked bits (ascending), int32 and int64, ragged
+    lengths, empty / full / single-bit words."""
+    rng = np.random.default_rng(5)
+    cases = [np.zeros(0, np.uint32), np.zeros(7, np.uint32), np.full(5, 0xffffffff, np.uint32),
+             np.array([1, 0x80000000, 0x00010000, 0x0000ffff, 0xffff0000], np.uint32)]
+    for nw in (1, 2, 31, 33, 1000, 6241):
+        cases.append(rng.integers(0, 2**32, nw, dtype=np.uint64).astype(np.uint32))
+        cases.append((rng.integers(0, 2**32, nw, dtype=np.uint64) & rng.integers(0, 2**32, nw, dtype=np.uint64)
+                      & rng.integers(0, 2**32, nw, dtype=np.uint64)).astype(np.uint32))
+    for w in cases:
+        want = np.flatnonzero(np.unpackbits(w.view(np.uint8), bitorder='little'))
+        for width in (4, 8):
+            assert np.array_equal(_expand(w, width), want)
+
+
+def test_expand_words_portable_path():
+    """Same check with the AVX-512 path switched off (fresh process: the choice is cached)."""
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tests.test_host_logic import _expand\n"
+            "w = np.random.default_rng(1).integers(0, 2**32, 777, dtype=np.uint64).astype(np.uint32)\n"
+            "want = np.flatnonzero(np.unpackbits(w.view(np.uint8), bitorder='little'))\n"
+            "assert np.array_equal(_expand(w, 4), want) and np.array_equal(_expand(w, 8), want)\n") % ROOT
+    env = dict(os.environ, FLUXB200_NO_AVX512='1')
+    subprocess.run([sys.executable, '-c', code], check=True, env=env, cwd=ROOT)
 
 
 def test_slab_plan():

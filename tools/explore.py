@@ -2,8 +2,11 @@
 import sys, time
 import numpy as np
 sys.path.insert(0, '.')
+import os
 import fluxpy_b200
-from fluxpy_b200 import meshes, form_factors
+from fluxpy_b200 import meshes, form_factors, _lib
+if os.environ.get('FLUXB200_SO'):  # A/B against another build of the library
+    _lib.SO_PATH = os.path.abspath(os.environ['FLUXB200_SO'])
 
 def run(n, rows, dtype=np.float32, opts=()):
     V, F = meshes.gaussian_crater(n, 0, dtype=dtype)
@@ -24,6 +27,10 @@ def run(n, rows, dtype=np.float32, opts=()):
 
 if __name__ == '__main__':
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'ab':
+        run(317, 4096)
+        run(159, 4096)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'quick':
         run(317, 4096)
         run(317, 4096, opts=(('blocks_per_sm', 4),))

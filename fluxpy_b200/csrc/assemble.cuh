@@ -73,7 +73,32 @@ template <class T> struct TraceArgs {
     int shaft_filter;               // 0: test every record of the per-unit list (A/B check)
 };
 
+// explicit shared-space loads / stores from a 32-bit shared address kept in a register: the
+// generic-pointer form makes ptxas rebuild the address (thread id, cluster CTA id, window base)
+// inside the hot loops
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_i1(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_i1(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 constexpr int kLeafCap = 8; // deferred candidate triangles per lane
+#ifndef FB_TRACE_MIN_BLOCKS
+#define FB_TRACE_MIN_BLOCKS 4 // resident CTAs per SM the register budget is cut for (64 registers)
+#endif
 
 // K4, persistent and warp-centric.  A work unit is one (row, chunk of 1024
 // Morton-ordered columns); every warp of the grid pulls units from one global
@@ -98,19 +123,22 @@ constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 // top-down traversal from the root only); it is kept as the measured
 // alternative and as an independent check of the path walk.
 template <class T, bool kTop>
-__global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs<T> A) {
+__global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kernel(const TraceArgs<T> A) {
     extern __shared__ float4 smem_top[];
     __shared__ uint32_t words_s[kTraceWarps][32];
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
     __shared__ float4 path_s[kTop ? 1 : kTraceWarps][kTop ? 1 : 3 * kStackDepth];
     __shared__ int2 range_s[kTop ? 1 : kTraceWarps][kTop ? 1 : kStackDepth];
-    __shared__ unsigned char sel_s[kTop ? 1 : kTraceWarps][kTop ? 1 : kStackDepth];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     if (kTop) {
         for (int k = threadIdx.x; k < 6 * A.ntop; k += kTraceThreads) smem_top[k] = __ldg(A.nodes + k);
         __syncthreads();
     }
     const BvhView bvh{A.nodes, smem_top, A.tri, kTop ? A.ntop : 0, A.ninternal, A.nfaces, A.error_flag};
+    uint32_t path_base = (uint32_t)__cvta_generic_to_shared(&path_s[warp][0]);
+    uint32_t range_base = (uint32_t)__cvta_generic_to_shared(&range_s[warp][0]);
+    uint32_t leaf_base = (uint32_t)__cvta_generic_to_shared(&leaf_s[0][tid]);
+    asm volatile("" : "+r"(path_base), "+r"(range_base), "+r"(leaf_base)); // keep them: do not rematerialise
     const unsigned total_units = (unsigned)A.m * (unsigned)A.nchunks;
     unsigned long long tested = 0;
 
@@ -130,6 +158,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         // uniform loop with broadcast shared-memory loads instead of descending from the root.
         int npath = 0;
         int cref = -0x7fffffff; // common ancestor of the chunk's targets when usable (see below)
+        int xdrop = -1;         // list entry of X when every target of the chunk is under it (cref valid)
         if (!kTop && A.ninternal > 0) {
             const int ileaf = A.face_leaf[i];
             int code = A.leaf_up[ileaf];
@@ -186,6 +215,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 if (complete) {
                     npath = n2;
                     cref = c;
+                    xdrop = xe;
                 }
                 __syncwarp();
             }
@@ -217,7 +247,11 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
         // chunk's target centroids.  A source-path record whose (padded) box or fitted slab is
         // separated from that hull along x, y, z or its own slab direction cannot be hit by
         // any of them: drop it for the whole unit.  Records holding targets always stay.
-        int nsel = 0;
+        // The list is then partitioned in place: [records that passed] [records that did not] and, when
+        // every target of the chunk lies under one record X (cref valid), X itself is taken out -- its
+        // inside is covered by the upward walk -- so that the uniform loop over the first nsel (or, for
+        // a batch that needs the unfiltered list, nall) records is a plain walk with no per-record checks.
+        int nsel = 0, nall = npath;
         if (!kTop && npath > 0) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -231,26 +265,51 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             const float h0l = fminf(px, bl0) - pad, h0h = fmaxf(px, bh0) + pad;
             const float h1l = fminf(py, bl1) - pad, h1h = fmaxf(py, bh1) + pad;
             const float h2l = fminf(pz, bl2) - pad, h2h = fmaxf(pz, bh2) + pad;
-            for (int e0 = 0; e0 < npath; e0 += 32) {
-                const int e = e0 + lane;
-                bool keepr = false;
+            static_assert(kStackDepth <= 64, "the list is partitioned two entries per lane");
+            float4 ra[2], rb2[2], rc[2];
+            int2 rr[2];
+            bool keepr[2], other[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = h * 32 + lane;
+                keepr[h] = other[h] = false;
                 if (e < npath) {
                     const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
                     const int2 rg = range_s[warp][e];
-                    keepr = true;
+                    ra[h] = a; rb2[h] = b; rc[h] = cc; rr[h] = rg;
+                    bool keep = true;
                     if (A.shaft_filter && (rg.y < leaf_lo || rg.x > leaf_hi)) { // holds no target of this chunk
-                        if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keepr = false;
+                        if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keep = false;
                         // extent of the hull along the slab direction
                         const float sp = cc.x * px + cc.y * py + cc.z * pz;
                         const float lo_s = fminf(cc.x * bl0, cc.x * bh0) + fminf(cc.y * bl1, cc.y * bh1) + fminf(cc.z * bl2, cc.z * bh2);
                         const float hi_s = fmaxf(cc.x * bl0, cc.x * bh0) + fmaxf(cc.y * bl1, cc.y * bh1) + fmaxf(cc.z * bl2, cc.z * bh2);
                         const float spad = pad * (fabsf(cc.x) + fabsf(cc.y) + fabsf(cc.z));
-                        if (fminf(sp, lo_s) - spad > cc.w || fmaxf(sp, hi_s) + spad < b.w) keepr = false;
+                        if (fminf(sp, lo_s) - spad > cc.w || fmaxf(sp, hi_s) + spad < b.w) keep = false;
+                    }
+                    if (e != xdrop) {
+                        keepr[h] = keep;
+                        other[h] = !keep;
                     }
                 }
-                const uint32_t kb = __ballot_sync(0xffffffffu, keepr);
-                if (keepr) sel_s[warp][nsel + __popc(kb & ((1u << lane) - 1u))] = (unsigned char)e;
-                nsel += __popc(kb);
+            }
+            const uint32_t kb0 = __ballot_sync(0xffffffffu, keepr[0]), kb1 = __ballot_sync(0xffffffffu, keepr[1]);
+            const uint32_t ob0 = __ballot_sync(0xffffffffu, other[0]), ob1 = __ballot_sync(0xffffffffu, other[1]);
+            const uint32_t lt = (1u << lane) - 1u;
+            nsel = __popc(kb0) + __popc(kb1);
+            nall = nsel + __popc(ob0) + __popc(ob1);
+            __syncwarp(); // every lane holds its two records: the list can be rewritten
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int d = -1;
+                if (keepr[h]) d = (h ? __popc(kb0) : 0) + __popc((h ? kb1 : kb0) & lt);
+                else if (other[h]) d = nsel + (h ? __popc(ob0) : 0) + __popc((h ? ob1 : ob0) & lt);
+                if (d >= 0) {
+                    path_s[warp][3 * d] = ra[h];
+                    path_s[warp][3 * d + 1] = rb2[h];
+                    path_s[warp][3 * d + 2] = rc[h];
+                    range_s[warp][d] = rr[h];
+                }
             }
             __syncwarp();
         }
@@ -277,7 +336,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             const uint32_t wk = __shfl_sync(0xffffffffu, myword, k);
             const uint32_t before = __shfl_sync(0xffffffffu, incl - __popc(myword), k);
             // ---- ray set-up and the target's own hit distance (converged) ----------
-            Ray ray;
+            Ray ray = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f};
             int bit = 0, tleaf = -1, tface = 0;
             float tj = 0.f;
             bool active = false, blocked = false, overshoot = false;
@@ -312,7 +371,7 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
             int stack[kStackDepth];
             int sp = 0, node = 0, nl = 0;
             auto push_leaf = [&](int leaf) {
-                if (nl < kLeafCap) leaf_s[nl++][tid] = leaf;
+                if (nl < kLeafCap) sts_i1(leaf_base + (uint32_t)(nl++) * (uint32_t)(sizeof(int) * kTraceThreads), leaf);
                 else if (leaf_occludes_cold(A.tri, ray, tj, leaf, tface)) {
                     blocked = true;
                     active = false;
@@ -329,17 +388,30 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
                 // covered by phase B.
                 int xref = ~tleaf;
                 const bool fullpath = __any_sync(0xffffffffu, active && overshoot);
-                const int nuse = fullpath ? npath : nsel;
-                for (int ks = 0; ks < nuse; ++ks) {
-                    const int e = fullpath ? ks : (int)sel_s[warp][ks];
-                    const float4 a = path_s[warp][3 * e], b = path_s[warp][3 * e + 1], cc = path_s[warp][3 * e + 2];
-                    const int2 rg = range_s[warp][e];
-                    const int ref = __float_as_int(a.w);
-                    if (tleaf >= rg.x && tleaf <= rg.y) {
-                        xref = ref;
-                    } else if (active && child_hit(ray, rb, a, b, cc, tmax)) {
-                        if (ref < 0) push_leaf(~ref);
-                        else push_node(ref);
+                const int nuse = fullpath ? nall : nsel;
+                const float tmax_a = active ? tmax : -1.0f; // a lane without a ray never hits
+                if (cref != -0x7fffffff) { // X is not in the list: nothing to check per record
+                    uint32_t addr = path_base;
+                    for (int ks = 0; ks < nuse; ++ks, addr += 48) {
+                        const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
+                        if (child_hit(ray, rb, a, b, cc, tmax_a)) {
+                            const int ref = __float_as_int(a.w);
+                            if (ref < 0) push_leaf(~ref);
+                            else push_node(ref);
+                        }
+                    }
+                } else { // the chunk straddles several records: every lane skips the one holding its target
+                    uint32_t addr = path_base, raddr = range_base;
+                    for (int ks = 0; ks < nuse; ++ks, addr += 48, raddr += 8) {
+                        const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
+                        const int2 rg = lds_i2(raddr);
+                        const int ref = __float_as_int(a.w);
+                        if (tleaf >= rg.x && tleaf <= rg.y) {
+                            xref = ref;
+                        } else if (child_hit(ray, rb, a, b, cc, tmax_a)) {
+                            if (ref < 0) push_leaf(~ref);
+                            else push_node(ref);
+                        }
                     }
                 }
                 // phase B: from the target leaf up to X (or the chunk's common ancestor), the
@@ -386,7 +458,8 @@ __global__ void __launch_bounds__(kTraceThreads, 4) trace_kernel(const TraceArgs
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 for (int q = 0; q < mx; ++q)
-                    if (q < nl && !blocked) blocked = leaf_occludes(bvh, ray, tj, leaf_s[q][tid], tface);
+                    if (q < nl && !blocked)
+                        blocked = leaf_occludes(bvh, ray, tj, lds_i1(leaf_base + (uint32_t)q * (uint32_t)(sizeof(int) * kTraceThreads)), tface);
             }
             if (blocked) atomicAnd(&words_s[warp][k], ~(1u << bit));
         }

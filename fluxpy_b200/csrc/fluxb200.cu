@@ -451,9 +451,9 @@ template <class T> void launch_fill(fluxb200_mesh *M, size_t row0, size_t mr, co
     A.data = data;
     A.indices = indices;
     A.index_width = index_width;
-    // enough CTAs (8 rows x one column segment each) to fill the machine about four times over
+    // enough CTAs (8 rows x one column segment each) for about four waves of four resident CTAs per SM
     const int64_t row_blocks = ceil_div((int64_t)mr, kFillWarps), ngroups = ceil_div(nwords, 32);
-    const int64_t segs = std::max<int64_t>(1, std::min<int64_t>(ngroups, ceil_div(4 * (int64_t)M->num_sms, row_blocks)));
+    const int64_t segs = std::max<int64_t>(1, std::min<int64_t>(ngroups, ceil_div(16 * (int64_t)M->num_sms, row_blocks)));
     FB_CUDA(cudaFuncSetAttribute(emit_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)emit_smem_bytes<T>()));
     emit_kernel<T><<<dim3((unsigned)row_blocks, (unsigned)segs), kFillThreads, emit_smem_bytes<T>(), st>>>(A);

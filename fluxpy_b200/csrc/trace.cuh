@@ -148,7 +148,7 @@ __device__ __forceinline__ RayBox make_raybox(const Ray &r) {
 // child = (a: lo.xyz | ref) (b: hi.xyz | slab_min) (c: slab_dir.xyz | slab_max)
 // AABB slab test on [0, tmax] intersected with the fitted-slab interval.  Boxes
 // and slab extents are padded at build time; the final comparison carries one
-// more relative + absolute guard band.
+// more relative guard band.
 #ifndef FB_TEST_ORDER
 #define FB_TEST_ORDER 0 // 0: box and slab together; 1: slab first, early out; 2: box first, early out
 #endif
@@ -165,14 +165,14 @@ __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const 
     float tn = fmaxf(fminf(s0, s1), 0.0f);
     float tf = fminf(fmaxf(s0, s1), tmax);
 #if FB_TEST_ORDER == 1
-    if (!(tn <= fmaf(tf, 1.000002f, 1e-30f))) return false;
+    if (!(tn <= tf * 1.000002f)) return false;
 #endif
     const float x0 = fmaf(a.x, rb.ix, -rb.ox), x1 = fmaf(b.x, rb.ix, -rb.ox);
     const float y0 = fmaf(a.y, rb.iy, -rb.oy), y1 = fmaf(b.y, rb.iy, -rb.oy);
     const float z0 = fmaf(a.z, rb.iz, -rb.oz), z1 = fmaf(b.z, rb.iz, -rb.oz);
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tn));
     tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tf));
-    return tn <= fmaf(tf, 1.000002f, 1e-30f);
+    return tn <= tf * 1.000002f;
 }
 
 template <bool kTop = true>

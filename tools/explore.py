@@ -27,6 +27,10 @@ def run(n, rows, dtype=np.float32, opts=()):
 
 if __name__ == '__main__':
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'ab3':
+        run(317, 4096, opts=(('blocks_per_sm', 3),))
+        run(159, 4096, opts=(('blocks_per_sm', 3),))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'ab':
         run(317, 4096)
         run(159, 4096)

@@ -208,6 +208,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL prints its version banner on stdout: one JSON line only
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus or world == 1, 'launch one rank per GPU (torchrun)'
 

@@ -633,7 +633,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
             const char *lws = getenv("LOCAL_WORLD_SIZE");
             const int ranks = std::max(1, lws ? atoi(lws) : 1);
             const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-            nthreads = std::min(8, std::max(1, hw / (2 * ranks)));
+            nthreads = std::min(8, std::max(1, hw / ranks - 1)); // one core per rank stays with the submitting thread
         }
         M->expander.start(nthreads);
         M->h_jbits.reserve(sizeof(uint32_t) * slot_words * fluxb200_mesh::kHostSlots);

@@ -32,23 +32,46 @@ template <class Index> int64_t expand_scalar(const uint32_t *words, int nwords, 
 }
 
 #if defined(__x86_64__)
-// 16 column positions per step: compress the lane ids selected by 16 mask bits, masked store
-__attribute__((target("avx512f"))) int64_t expand_avx512(const uint32_t *words, int nwords, int32_t *out) {
+// 16 column positions per step: compress the lane ids selected by 16 mask bits.  Full 64-byte
+// stores while at least 16 entries of the row are still to come (what they write past the
+// compressed ids is overwritten by the next store), masked stores for the last entries so that
+// nothing is ever written outside the row (another thread owns the next row).
+__attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *words, int nwords, int32_t *out,
+                                                         int64_t row_entries) {
     int32_t *dst = out;
+    int32_t *const safe_end = out + (row_entries - 16); // full stores allowed while dst <= safe_end
     const __m512i lanes = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+    const __m512i sixteen = _mm512_set1_epi32(16);
     for (int k = 0; k < nwords; ++k) {
         const uint32_t w = words[k];
         if (!w) continue;
         const __m512i base = _mm512_add_epi32(lanes, _mm512_set1_epi32(k * 32));
         const __mmask16 lo = (__mmask16)(w & 0xffffu), hi = (__mmask16)(w >> 16);
         const int clo = __builtin_popcount(lo), chi = __builtin_popcount(hi);
-        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << clo) - 1u), _mm512_maskz_compress_epi32(lo, base));
-        dst += clo;
-        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << chi) - 1u),
-                                 _mm512_maskz_compress_epi32(hi, _mm512_add_epi32(base, _mm512_set1_epi32(16))));
-        dst += chi;
+        const __m512i vlo = _mm512_maskz_compress_epi32(lo, base);
+        const __m512i vhi = _mm512_maskz_compress_epi32(hi, _mm512_add_epi32(base, sixteen));
+        if (dst + clo <= safe_end) {
+            _mm512_storeu_si512(dst, vlo);
+            _mm512_storeu_si512(dst + clo, vhi);
+        } else {
+            _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << clo) - 1u), vlo);
+            _mm512_mask_storeu_epi32(dst + clo, (__mmask16)((1u << chi) - 1u), vhi);
+        }
+        dst += clo + chi;
     }
     return (int64_t)(dst - out);
+}
+
+__attribute__((target("popcnt"))) int64_t count_bits_popcnt(const uint32_t *w, int n) {
+    int64_t c = 0;
+    int k = 0;
+    for (; k + 2 <= n; k += 2) {
+        uint64_t two;
+        memcpy(&two, w + k, 8);
+        c += __builtin_popcountll(two);
+    }
+    for (; k < n; ++k) c += __builtin_popcount(w[k]);
+    return c;
 }
 #endif
 
@@ -64,10 +87,23 @@ bool have_avx512() {
 
 } // namespace
 
-int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out) {
+int64_t count_bits(const uint32_t *words, int nwords) {
+#if defined(__x86_64__)
+    static const bool hw = __builtin_cpu_supports("popcnt");
+    if (hw) return count_bits_popcnt(words, nwords);
+#endif
+    int64_t c = 0;
+    for (int k = 0; k < nwords; ++k) c += __builtin_popcount(words[k]);
+    return c;
+}
+
+int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out, int64_t row_entries) {
     if (index_width == 8) return expand_scalar<int64_t>(words, nwords, reinterpret_cast<int64_t *>(out));
 #if defined(__x86_64__)
-    if (have_avx512()) return expand_avx512(words, nwords, reinterpret_cast<int32_t *>(out));
+    if (have_avx512()) {
+        if (row_entries < 0) row_entries = count_bits(words, nwords); // not known: count first
+        return expand_avx512(words, nwords, reinterpret_cast<int32_t *>(out), row_entries);
+    }
 #endif
     return expand_scalar<int32_t>(words, nwords, reinterpret_cast<int32_t *>(out));
 }
@@ -115,14 +151,13 @@ void HostExpander::run() {
         const size_t r1 = t->mr * (size_t)(item.second + 1) / (size_t)t->pieces;
         for (size_t r = r0; r < r1; ++r) {
             const uint32_t *w = t->words + r * (size_t)t->nwords;
-            int64_t bits = 0;
-            for (int k = 0; k < t->nwords; ++k) bits += __builtin_popcount(w[k]);
+            const int64_t bits = count_bits(w, t->nwords);
             if (bits != t->offs[r + 1] - t->offs[r]) { // never write outside the row's range
                 t->mismatch.store(1);
                 continue;
             }
             char *dst = reinterpret_cast<char *>(t->indices) + (size_t)t->index_width * (size_t)t->offs[r];
-            expand_words(w, t->nwords, t->index_width, dst);
+            expand_words(w, t->nwords, t->index_width, dst, bits);
         }
         if (t->pending.fetch_sub(1) == 1) {
             std::lock_guard<std::mutex> lk(mu_); // pairs with the predicate check in wait()

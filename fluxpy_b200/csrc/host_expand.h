@@ -11,8 +11,12 @@
 
 namespace fluxb200 {
 
-// positions of the set bits of words[0..nwords), ascending, as int32 or int64; returns how many
-int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out);
+// positions of the set bits of words[0..nwords), ascending, as int32 or int64; returns how many.
+// row_entries = popcount of the words if the caller knows it (-1: counted here); exactly that many
+// entries of `out` are written, never more.
+int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out, int64_t row_entries = -1);
+
+int64_t count_bits(const uint32_t *words, int nwords);
 
 // the rows of one sub-slab: words (mr x nwords, host) -> indices[offs[r] .. offs[r+1])
 struct ExpandTask {

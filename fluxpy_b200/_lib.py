@@ -29,7 +29,7 @@ EXPORTS = (
     'fluxb200_csr_extract', 'fluxb200_csr_matmat',
     'fluxb200_visibility', 'fluxb200_is_occluded', 'fluxb200_intersect1',
     'fluxb200_visibility_bruteforce', 'fluxb200_slab_plan', 'fluxb200_mesh_stream',
-    'fluxb200_set_option', 'fluxb200_expand_words',
+    'fluxb200_set_option', 'fluxb200_expand_words', 'fluxb200_expand_rows',
 )
 
 
@@ -116,6 +116,7 @@ def lib():
     L.fluxb200_mesh_stream.argtypes = [vp, pp]
     L.fluxb200_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     L.fluxb200_expand_words.argtypes = [vp, sz, i32, vp, ctypes.POINTER(i64)]
+    L.fluxb200_expand_rows.argtypes = [vp, sz, sz, vp, i32, vp, i32]
     for name in EXPORTS:
         if name != 'fluxb200_last_error' and name != 'fluxb200_abi_version':
             getattr(L, name).restype = i32

@@ -1462,6 +1462,32 @@ int fluxb200_expand_words(const uint32_t *words, size_t nwords, int index_width,
     });
 }
 
+int fluxb200_expand_rows(const uint32_t *words, size_t nwords, size_t mr, const int64_t *offs, int index_width,
+                         void *indices, int nthreads) {
+    return guarded([&] {
+        FB_REQUIRE((words || !nwords || !mr) && offs && (indices || offs[mr] == offs[0]), "NULL argument");
+        FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
+        FB_REQUIRE(nwords < (1ull << 26) && nthreads >= 0 && nthreads <= 64, "argument out of range");
+        if (!mr) return;
+        HostExpander pool; // the same worker pool fluxb200_ff_assemble feeds from its copy-out callbacks
+        if (nthreads == 0) nthreads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        pool.start(nthreads);
+        ExpandTask t;
+        t.words = words;
+        t.nwords = (int)nwords;
+        t.mr = mr;
+        t.offs.assign(offs, offs + mr + 1);
+        t.indices = indices;
+        t.index_width = index_width;
+        t.pieces = (int)std::max<size_t>(1, std::min<size_t>(mr, 2 * (size_t)nthreads));
+        t.pending.store(t.pieces);
+        t.owner = &pool;
+        pool.submit(&t);
+        pool.wait(&t);
+        FB_REQUIRE(t.mismatch.load() == 0, "a row's set bits do not match its CSR row length");
+    });
+}
+
 int fluxb200_mesh_stream(fluxb200_mesh *M, void **stream) {
     return guarded([&] {
         FB_REQUIRE(M && stream, "NULL argument");

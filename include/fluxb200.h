@@ -219,6 +219,12 @@ int fluxb200_slab_plan(size_t m, int nranks, const int64_t *weights, int64_t *st
 int fluxb200_expand_words(const uint32_t *words, size_t nwords, int index_width, void *out,
                           int64_t *count);
 
+/* The same for `mr` rows at once on `nthreads` host threads (0 = automatic): words is mr x nwords,
+ * row r goes to indices[offs[r] .. offs[r+1]).  A row whose set bits do not match its length is
+ * reported as an error and left unwritten.  This is the worker pool fluxb200_ff_assemble uses. */
+int fluxb200_expand_rows(const uint32_t *words, size_t nwords, size_t mr, const int64_t *offs,
+                         int index_width, void *indices, int nthreads);
+
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, so a
  * caller can bracket calls with its own events. */
 int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);

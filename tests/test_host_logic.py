@@ -83,14 +83,63 @@ def test_expand_words_matches_numpy():
             assert np.array_equal(_expand(w, width), want)
 
 
-def test_expand_words_portable_path():
-    """Same check with the AVX-512 path switched off (fresh process: the choice is cached)."""
-    code = ("import numpy as np, sys; sys.path.insert(0, %r); from tests.test_host_logic import _expand\n"
-            "w = np.random.default_rng(1).integers(0, 2**32, 777, dtype=np.uint64).astype(np.uint32)\n"
-            "want = np.flatnonzero(np.unpackbits(w.view(np.uint8), bitorder='little'))\n"
-            "assert np.array_equal(_expand(w, 4), want) and np.array_equal(_expand(w, 8), want)\n") % ROOT
+def test_expand_words_any_alignment_and_no_stray_writes():
+    """The AVX-512 path writes whole 64-byte lines with streaming stores between a masked head and a
+    masked tail: every start alignment, rows shorter than a line, guards on both sides."""
+    from fluxpy_b200 import _lib
+    rng = np.random.default_rng(9)
+    for nw in (1, 2, 5, 40, 700):
+        for dens in (0.02, 0.5, 1.0):
+            bits = rng.random(nw*32) < dens
+            w = np.packbits(bits, bitorder='little').view(np.uint32)
+            want = np.flatnonzero(bits)
+            for shift in range(17):
+                buf = np.full(len(want) + 64, -7, np.int32)
+                out = buf[16 + shift:]
+                cnt = ctypes.c_int64(-1)
+                _lib.check(_lib.lib().fluxb200_expand_words(_lib.ptr(w), len(w), 4, out.ctypes.data_as(ctypes.c_void_p),
+                                                            ctypes.byref(cnt)))
+                assert cnt.value == len(want) and np.array_equal(out[:len(want)], want)
+                assert (buf[:16 + shift] == -7).all() and (out[len(want):] == -7).all()
+
+
+def test_expand_rows_thread_pool():
+    """The worker pool of the copy-out: ragged rows packed back to back (so neighbouring rows share
+    cache lines across threads), 1 to 5 threads, int32 and int64; a wrong row length is an error."""
+    from fluxpy_b200 import _lib
+    rng = np.random.default_rng(12)
+    nw, mr = 97, 301
+    dens = rng.random(mr)**2
+    bits = rng.random((mr, nw*32)) < dens[:, None]
+    bits[5] = False
+    bits[7] = True
+    words = np.ascontiguousarray(np.packbits(bits, axis=1, bitorder='little')).view(np.uint32).reshape(mr, nw)
+    counts = bits.sum(1)
+    offs = np.zeros(mr + 1, np.int64)
+    np.cumsum(counts, out=offs[1:])
+    offs += 3                                        # unaligned start
+    want = np.concatenate([np.flatnonzero(b) for b in bits])
+    for width, dt in ((4, np.int32), (8, np.int64)):
+        for nthreads in (1, 2, 5, 0):
+            out = np.full(int(offs[-1]) + 40, -7, dt)
+            _lib.check(_lib.lib().fluxb200_expand_rows(_lib.ptr(words), nw, mr, _lib.ptr(offs), width, _lib.ptr(out),
+                                                       nthreads))
+            assert np.array_equal(out[3:int(offs[-1])], want)
+            assert (out[:3] == -7).all() and (out[int(offs[-1]):] == -7).all()
+    bad = offs.copy()
+    bad[100:] += 1                                   # row 99 one entry too long
+    out = np.full(int(bad[-1]) + 40, -7, np.int32)
+    with pytest.raises(RuntimeError, match='do not match'):
+        _lib.check(_lib.lib().fluxb200_expand_rows(_lib.ptr(words), nw, mr, _lib.ptr(bad), 4, _lib.ptr(out), 3))
+
+
+def test_expand_portable_path():
+    """The same checks with the AVX-512 path switched off (fresh process: the choice is cached)."""
     env = dict(os.environ, FLUXB200_NO_AVX512='1')
-    subprocess.run([sys.executable, '-c', code], check=True, env=env, cwd=ROOT)
+    out = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', os.path.abspath(__file__), '-k',
+                          'matches_numpy or any_alignment or thread_pool'], env=env, cwd=ROOT,
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and '3 passed' in out.stdout, out.stdout + out.stderr
 
 
 def test_slab_plan():

@@ -1,0 +1,403 @@
+/* k4_model.c -- CPU model of the trace kernel's traversal (K4, fluxpy_b200/csrc/assemble.cuh), for
+ * counting work, not for results.  It rebuilds the LBVH the way lbvh.cuh does (Morton codes of the box
+ * centres with one scale for all axes, Karras hierarchy, padded boxes, fitted slabs), then walks a sample
+ * of (row, chunk) work units exactly as the kernel does -- per-unit record list, shaft filter, batches of
+ * 32 surviving columns, phase A / B / C -- and reports the warp-level iteration counts per batch that
+ * decide the kernel's instruction count (it is issue-bound: profiles/r01b_kernels_ncu.md).  Design variants
+ * (chunk size, a second, per-batch shaft filter) are switches, so their effect on the counts can be read
+ * off without GPU time.  Not part of the product or of the oracle; nothing imports it.
+ *
+ *   gcc -O2 -shared -fPIC -o /tmp/libk4model.so tools/k4_model.c -lm     (tools/k4_model.py does this)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    int n;                 /* faces */
+    const float *V;        /* vertices */
+    const int *F;          /* faces */
+    const double *P, *N;   /* centroids, normals (per face) */
+    int *left, *right, *parent, *first, *last; /* Karras nodes: internal 0..n-2, leaf k -> n-1+k */
+    float *box;            /* 6 per node */
+    float *sdir, *smin, *smax; /* fitted slab per node */
+    int *leaf_face, *face_leaf;
+    uint64_t *keys;
+    float scale;
+} Model;
+
+static uint64_t spread21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+static const uint64_t *g_keys;
+static int cmp_key(const void *a, const void *b) {
+    const int x = *(const int *)a, y = *(const int *)b;
+    if (g_keys[x] != g_keys[y]) return g_keys[x] < g_keys[y] ? -1 : 1;
+    return x - y; /* stable, as the LSD radix sort */
+}
+
+static int delta(const uint64_t *keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __builtin_clz((unsigned)(i ^ j));
+    return __builtin_clzll(a ^ b);
+}
+
+Model *k4_build(int nv, const float *V, int nf, const int *F, const double *P, const double *N) {
+    (void)nv;
+    Model *M = calloc(1, sizeof(Model));
+    const int n = nf, nn = 2 * n - 1;
+    M->n = n; M->V = V; M->F = F; M->P = P; M->N = N;
+    M->left = malloc(sizeof(int) * n); M->right = malloc(sizeof(int) * n);
+    M->parent = malloc(sizeof(int) * nn); M->first = malloc(sizeof(int) * n); M->last = malloc(sizeof(int) * n);
+    M->box = malloc(sizeof(float) * 6 * nn); M->sdir = malloc(sizeof(float) * 3 * nn);
+    M->smin = malloc(sizeof(float) * nn); M->smax = malloc(sizeof(float) * nn);
+    M->leaf_face = malloc(sizeof(int) * n); M->face_leaf = malloc(sizeof(int) * n);
+    uint64_t *code = malloc(sizeof(uint64_t) * n);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, mx = 0.f;
+    for (int f = 0; f < n; ++f)
+        for (int k = 0; k < 3; ++k) {
+            const float a = V[3 * F[3 * f] + k], b = V[3 * F[3 * f + 1] + k], c = V[3 * F[3 * f + 2] + k];
+            const float l = fminf(fminf(a, b), c), h = fmaxf(fmaxf(a, b), c), ce = 0.5f * (l + h);
+            lo[k] = fminf(lo[k], ce); hi[k] = fmaxf(hi[k], ce);
+            mx = fmaxf(mx, fmaxf(fabsf(l), fabsf(h)));
+        }
+    M->scale = mx;
+    const double ext = fmax(fmax((double)hi[0] - lo[0], (double)hi[1] - lo[1]), (double)hi[2] - lo[2]);
+    for (int f = 0; f < n; ++f) {
+        uint64_t c64 = 0;
+        for (int k = 0; k < 3; ++k) {
+            const float a = V[3 * F[3 * f] + k], b = V[3 * F[3 * f + 1] + k], c = V[3 * F[3 * f + 2] + k];
+            const double ce = 0.5f * (fminf(fminf(a, b), c) + fmaxf(fmaxf(a, b), c));
+            double u = ext > 0 ? (ce - lo[k]) / ext : 0.0;
+            u = fmin(fmax(u, 0.0), 1.0);
+            c64 |= spread21((uint64_t)fmin(u * 2097152.0, 2097151.0)) << (2 - k);
+        }
+        code[f] = c64;
+    }
+    for (int f = 0; f < n; ++f) M->leaf_face[f] = f;
+    g_keys = code;
+    qsort(M->leaf_face, n, sizeof(int), cmp_key);
+    M->keys = malloc(sizeof(uint64_t) * n);
+    for (int k = 0; k < n; ++k) { M->keys[k] = code[M->leaf_face[k]]; M->face_leaf[M->leaf_face[k]] = k; }
+    free(code);
+    const uint64_t *keys = M->keys;
+    for (int x = 0; x < nn; ++x) M->parent[x] = -1;
+    for (int i = 0; i < n - 1; ++i) { /* karras_kernel */
+        const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+        const int dmin = delta(keys, n, i, i - d);
+        int lmax = 2;
+        while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t >= 1; t >>= 1)
+            if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+        const int j = i + l * d, dnode = delta(keys, n, i, j);
+        int s = 0, t = l;
+        do {
+            t = (t + 1) >> 1;
+            if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        } while (t > 1);
+        const int gamma = i + s * d + (d < 0 ? d : 0);
+        const int lo_ = i < j ? i : j, hi_ = i < j ? j : i;
+        const int lc = (lo_ == gamma) ? (n - 1) + gamma : gamma;
+        const int rc = (hi_ == gamma + 1) ? (n - 1) + gamma + 1 : gamma + 1;
+        M->left[i] = lc; M->right[i] = rc; M->parent[lc] = i; M->parent[rc] = i;
+        M->first[i] = lo_; M->last[i] = hi_;
+    }
+    M->parent[0] = -1;
+    /* leaf boxes + area normals, then bottom-up by decreasing depth: process internal nodes in an order
+     * where children come first = sort by subtree size is overkill; use a post-order stack walk */
+    float *an = malloc(sizeof(float) * 3 * nn);
+    const float pad = 1.0e-6f * mx + 1e-30f;
+    for (int k = 0; k < n; ++k) {
+        const int f = M->leaf_face[k], x = n - 1 + k;
+        const float *v0 = V + 3 * F[3 * f], *v1 = V + 3 * F[3 * f + 1], *v2 = V + 3 * F[3 * f + 2];
+        for (int c = 0; c < 3; ++c) {
+            M->box[6 * x + c] = fminf(fminf(v0[c], v1[c]), v2[c]) - pad;
+            M->box[6 * x + 3 + c] = fmaxf(fmaxf(v0[c], v1[c]), v2[c]) + pad;
+        }
+        const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+        const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+        an[3 * x] = e1y * e2z - e1z * e2y; an[3 * x + 1] = e1z * e2x - e1x * e2z; an[3 * x + 2] = e1x * e2y - e1y * e2x;
+    }
+    if (n > 1) {
+        int *stack = malloc(sizeof(int) * 2 * nn), sp = 0;
+        char *seen = calloc(nn, 1);
+        stack[sp++] = 0;
+        while (sp) {
+            const int x = stack[sp - 1];
+            if (x >= n - 1) { --sp; continue; }
+            if (!seen[x]) { seen[x] = 1; stack[sp++] = M->left[x]; stack[sp++] = M->right[x]; continue; }
+            --sp;
+            const int lc = M->left[x], rc = M->right[x];
+            for (int c = 0; c < 3; ++c) {
+                M->box[6 * x + c] = fminf(M->box[6 * lc + c], M->box[6 * rc + c]);
+                M->box[6 * x + 3 + c] = fmaxf(M->box[6 * lc + 3 + c], M->box[6 * rc + 3 + c]);
+                an[3 * x + c] = an[3 * lc + c] + an[3 * rc + c];
+            }
+        }
+        free(stack); free(seen);
+    }
+    for (int x = 0; x < nn; ++x) {
+        const float ax = an[3 * x], ay = an[3 * x + 1], az = an[3 * x + 2], l = sqrtf(ax * ax + ay * ay + az * az);
+        if (l > 1e-30f && isfinite(l)) { M->sdir[3 * x] = ax / l; M->sdir[3 * x + 1] = ay / l; M->sdir[3 * x + 2] = az / l; }
+        else { M->sdir[3 * x] = 0; M->sdir[3 * x + 1] = 0; M->sdir[3 * x + 2] = 1; }
+        M->smin[x] = INFINITY; M->smax[x] = -INFINITY;
+    }
+    free(an);
+    for (int k = 0; k < n; ++k) { /* slab_extent_kernel, every ancestor (slab_limit = inf) */
+        const int f = M->leaf_face[k];
+        int x = n - 1 + k;
+        while (x >= 0) {
+            const float *d = M->sdir + 3 * x;
+            for (int v = 0; v < 3; ++v) {
+                const float *p = V + 3 * F[3 * f + v];
+                const float t = d[0] * p[0] + d[1] * p[1] + d[2] * p[2];
+                M->smin[x] = fminf(M->smin[x], t); M->smax[x] = fmaxf(M->smax[x], t);
+            }
+            x = M->parent[x];
+        }
+    }
+    const float spad = 8.0e-6f * mx + 1e-30f;
+    for (int x = 0; x < nn; ++x) { M->smin[x] -= spad; M->smax[x] += spad; }
+    return M;
+}
+
+void k4_free(Model *M) {
+    free(M->left); free(M->right); free(M->parent); free(M->first); free(M->last); free(M->box); free(M->sdir);
+    free(M->smin); free(M->smax); free(M->leaf_face); free(M->face_leaf); free(M->keys); free(M);
+}
+
+typedef struct { float ox, oy, oz, dx, dy, dz, ix, iy, iz, qx, qy, qz, tmax; } Ray;
+
+static int node_hit(const Model *M, int x, const Ray *r) { /* child_hit of trace.cuh */
+    const float *b = M->box + 6 * x, *d = M->sdir + 3 * x;
+    const float no = d[0] * r->ox + d[1] * r->oy + d[2] * r->oz, nd = d[0] * r->dx + d[1] * r->dy + d[2] * r->dz;
+    const float rn = 1.0f / nd;
+    const float s0 = (M->smin[x] - no) * rn, s1 = (M->smax[x] - no) * rn;
+    float tn = fmaxf(fminf(s0, s1), 0.0f), tf = fminf(fmaxf(s0, s1), r->tmax);
+    const float x0 = b[0] * r->ix - r->qx, x1 = b[3] * r->ix - r->qx;
+    const float y0 = b[1] * r->iy - r->qy, y1 = b[4] * r->iy - r->qy;
+    const float z0 = b[2] * r->iz - r->qz, z1 = b[5] * r->iz - r->qz;
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tn));
+    tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tf));
+    return tn <= tf * 1.000002f;
+}
+
+static void node_range(const Model *M, int x, int *lo, int *hi) {
+    if (x >= M->n - 1) { *lo = *hi = x - (M->n - 1); }
+    else { *lo = M->first[x]; *hi = M->last[x]; }
+}
+static int sibling(const Model *M, int x) {
+    const int p = M->parent[x];
+    return M->left[p] == x ? M->right[p] : M->left[p];
+}
+
+/* out[]: 0 batches, 1 rays, 2 A warp-iterations, 3 B warp-iterations, 4 C warp-iterations, 5 A lane hits,
+ * 6 B lane-iterations, 7 C lane-iterations, 8 leaf candidates, 9 flush warp-iterations, 10 units,
+ * 11 list length before the filter (sum over units), 12 after the chunk filter, 13 A warp-iterations with
+ * the per-batch filter, 14 candidate pairs, 15 units with a usable common ancestor */
+/* projection of an AABB (lo, hi) on axis a: [*mn, *mx] */
+static void proj_box(const float *lo, const float *hi, const float *a, float *mn, float *mx) {
+    *mn = *mx = 0.f;
+    for (int k = 0; k < 3; ++k) {
+        const float p = a[k] * lo[k], q = a[k] * hi[k];
+        *mn += fminf(p, q); *mx += fmaxf(p, q);
+    }
+}
+
+void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps, int batch_filter, int axes, double *out) {
+    const int n = M->n, nchunks = (n + chunk - 1) / chunk;
+    int *list = malloc(sizeof(int) * 256), *surv = malloc(sizeof(int) * chunk);
+    int *stack = malloc(sizeof(int) * 32 * 128);
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int i = rows[ri], ileaf = M->face_leaf[i];
+        const double *Pi = M->P + 3 * i, *Ni = M->N + 3 * i;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s0 = c * chunk, s1 = (s0 + chunk < n ? s0 + chunk : n);
+            /* list: own record, siblings up to the root */
+            int npath = 0, x = n - 1 + ileaf;
+            list[npath++] = x;
+            while (M->parent[x] >= 0) { list[npath++] = sibling(M, x); x = M->parent[x]; }
+            const int leaf_lo = s0, leaf_hi = s1 - 1;
+            int xe = -1, cref = -1;
+            for (int e = 0; e < npath; ++e) { int lo, hi; node_range(M, list[e], &lo, &hi); if (lo <= leaf_lo && leaf_hi <= hi) xe = e; }
+            if (xe >= 0 && leaf_lo != leaf_hi) {
+                int cn = M->parent[n - 1 + leaf_lo];
+                while (!(M->first[cn] <= leaf_lo && leaf_hi <= M->last[cn])) cn = M->parent[cn];
+                int cur = cn, ok = 1;
+                while (cur != list[xe]) { if (M->parent[cur] < 0 || npath >= 250) { ok = 0; break; } list[npath++] = sibling(M, cur); cur = M->parent[cur]; }
+                if (ok) cref = cn; /* (an incomplete walk leaves extra records in this model's list: rare) */
+            }
+            /* cull + chunk bbox */
+            float bl[3] = {INFINITY, INFINITY, INFINITY}, bh[3] = {-INFINITY, -INFINITY, -INFINITY};
+            int ns = 0;
+            for (int s = s0; s < s1; ++s) {
+                const int j = M->leaf_face[s];
+                const double *Pj = M->P + 3 * j, *Nj = M->N + 3 * j;
+                for (int k = 0; k < 3; ++k) { bl[k] = fminf(bl[k], (float)Pj[k]); bh[k] = fmaxf(bh[k], (float)Pj[k]); }
+                const double dx = Pj[0] - Pi[0], dy = Pj[1] - Pi[1], dz = Pj[2] - Pi[2];
+                double a = Ni[0] * dx + Ni[1] * dy + Ni[2] * dz, b = -(Nj[0] * dx + Nj[1] * dy + Nj[2] * dz);
+                a = a > 0 ? a : 0; b = b > 0 ? b : 0;
+                if (j != i && (float)(a * b) > (float)eps) surv[ns++] = s;
+            }
+            out[14] += s1 - s0;
+            out[10] += 1; out[11] += npath; if (cref >= 0) out[15] += 1;
+            /* shaft filter -> sel (X removed when cref valid) */
+            const float px = (float)Pi[0], py = (float)Pi[1], pz = (float)Pi[2];
+            int sel[256], nsel = 0;
+            {
+                const float pad = 3e-5f * M->scale + 1e-4f * fmaxf(fmaxf(bh[0] - bl[0], bh[1] - bl[1]), bh[2] - bl[2]) + 2e-3f;
+                const float hl[3] = {fminf(px, bl[0]) - pad, fminf(py, bl[1]) - pad, fminf(pz, bl[2]) - pad};
+                const float hh[3] = {fmaxf(px, bh[0]) + pad, fmaxf(py, bh[1]) + pad, fmaxf(pz, bh[2]) + pad};
+                for (int e = 0; e < npath; ++e) {
+                    if (cref >= 0 && e == xe) continue;
+                    const int y = list[e]; int lo, hi; node_range(M, y, &lo, &hi);
+                    int keep = 1;
+                    if (hi < leaf_lo || lo > leaf_hi) {
+                        const float *b = M->box + 6 * y, *d = M->sdir + 3 * y;
+                        if (b[0] > hh[0] || b[3] < hl[0] || b[1] > hh[1] || b[4] < hl[1] || b[2] > hh[2] || b[5] < hl[2]) keep = 0;
+                        const float sp = d[0] * px + d[1] * py + d[2] * pz;
+                        const float lo_s = fminf(d[0] * bl[0], d[0] * bh[0]) + fminf(d[1] * bl[1], d[1] * bh[1]) + fminf(d[2] * bl[2], d[2] * bh[2]);
+                        const float hi_s = fmaxf(d[0] * bl[0], d[0] * bh[0]) + fmaxf(d[1] * bl[1], d[1] * bh[1]) + fmaxf(d[2] * bl[2], d[2] * bh[2]);
+                        const float spad = pad * (fabsf(d[0]) + fabsf(d[1]) + fabsf(d[2]));
+                        if (fminf(sp, lo_s) - spad > M->smax[y] || fmaxf(sp, hi_s) + spad < M->smin[y]) keep = 0;
+                    }
+                    if (keep && axes && (hi < leaf_lo || lo > leaf_hi)) {
+                        /* variant: two more separating axes, perpendicular to the source -> chunk direction:
+                         * the axis-aligned hull of a diagonal shaft is mostly empty */
+                        const float cx = 0.5f * (bl[0] + bh[0]) - px, cy = 0.5f * (bl[1] + bh[1]) - py, cz = 0.5f * (bl[2] + bh[2]) - pz;
+                        const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
+                        if (cl > 1e-20f) {
+                            const float d0[3] = {cx / cl, cy / cl, cz / cl};
+                            float u[3] = {-d0[1], d0[0], 0.f};
+                            float ul = sqrtf(u[0] * u[0] + u[1] * u[1]);
+                            if (ul < 1e-6f) { u[0] = 1.f; u[1] = 0.f; ul = 1.f; }
+                            u[0] /= ul; u[1] /= ul;
+                            const float w[3] = {d0[1] * u[2] - d0[2] * u[1], d0[2] * u[0] - d0[0] * u[2], d0[0] * u[1] - d0[1] * u[0]};
+                            const float *ax[2] = {u, w};
+                            const float *b = M->box + 6 * y;
+                            for (int t = 0; t < 2 && keep; ++t) {
+                                float hmn, hmx, rmn, rmx;
+                                proj_box(bl, bh, ax[t], &hmn, &hmx);
+                                const float sp2 = ax[t][0] * px + ax[t][1] * py + ax[t][2] * pz;
+                                hmn = fminf(hmn, sp2) - 2.f * pad; hmx = fmaxf(hmx, sp2) + 2.f * pad;
+                                proj_box(b, b + 3, ax[t], &rmn, &rmx);
+                                if (rmn > hmx || rmx < hmn) keep = 0;
+                            }
+                        }
+                    }
+                    if (keep) sel[nsel++] = y;
+                }
+            }
+            out[12] += nsel;
+            /* batches */
+            for (int b0 = 0; b0 < ns; b0 += 32) {
+                const int nb = ns - b0 < 32 ? ns - b0 : 32;
+                Ray ray[32]; int tleaf[32];
+                float tb_lo[3] = {INFINITY, INFINITY, INFINITY}, tb_hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                for (int l = 0; l < nb; ++l) {
+                    const int s = surv[b0 + l], j = M->leaf_face[s];
+                    const double *Pj = M->P + 3 * j;
+                    float dx = (float)(Pj[0] - Pi[0]), dy = (float)(Pj[1] - Pi[1]), dz = (float)(Pj[2] - Pi[2]);
+                    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                    dx /= nrm; dy /= nrm; dz /= nrm;
+                    Ray *r = &ray[l];
+                    r->dx = dx; r->dy = dy; r->dz = dz;
+                    r->ox = px + 1e-3f * dx; r->oy = py + 1e-3f * dy; r->oz = pz + 1e-3f * dz;
+                    r->ix = 1.0f / (fabsf(dx) < 1e-30f ? copysignf(1e-30f, dx) : dx);
+                    r->iy = 1.0f / (fabsf(dy) < 1e-30f ? copysignf(1e-30f, dy) : dy);
+                    r->iz = 1.0f / (fabsf(dz) < 1e-30f ? copysignf(1e-30f, dz) : dz);
+                    r->qx = r->ox * r->ix; r->qy = r->oy * r->iy; r->qz = r->oz * r->iz;
+                    r->tmax = (nrm - 1e-3f) * 1.000002f; /* the ray meets its target at the centroid */
+                    tleaf[l] = s;
+                    for (int k = 0; k < 3; ++k) { tb_lo[k] = fminf(tb_lo[k], (float)Pj[k]); tb_hi[k] = fmaxf(tb_hi[k], (float)Pj[k]); }
+                }
+                out[0] += 1; out[1] += nb;
+                /* phase A */
+                int sp[32] = {0}, cand[32] = {0}, xref[32];
+                int a_iter = 0, a_iter_bf = 0;
+                const float bpad = 3e-5f * M->scale + 1e-4f * fmaxf(fmaxf(tb_hi[0] - tb_lo[0], tb_hi[1] - tb_lo[1]), tb_hi[2] - tb_lo[2]) + 2e-3f;
+                for (int l = 0; l < nb; ++l) xref[l] = -2;
+                for (int e = 0; e < nsel; ++e) {
+                    const int y = sel[e]; int lo, hi; node_range(M, y, &lo, &hi);
+                    ++a_iter;
+                    /* per-batch filter (variant): drop the record for this batch if it is separated from the hull
+                     * of the source and the batch's targets along x, y, z or its slab direction */
+                    int bkeep = 1;
+                    if (hi < leaf_lo || lo > leaf_hi) {
+                        const float *b = M->box + 6 * y, *d = M->sdir + 3 * y;
+                        const float hl[3] = {fminf(px, tb_lo[0]) - bpad, fminf(py, tb_lo[1]) - bpad, fminf(pz, tb_lo[2]) - bpad};
+                        const float hh[3] = {fmaxf(px, tb_hi[0]) + bpad, fmaxf(py, tb_hi[1]) + bpad, fmaxf(pz, tb_hi[2]) + bpad};
+                        if (b[0] > hh[0] || b[3] < hl[0] || b[1] > hh[1] || b[4] < hl[1] || b[2] > hh[2] || b[5] < hl[2]) bkeep = 0;
+                        const float sp_ = d[0] * px + d[1] * py + d[2] * pz;
+                        const float lo_s = fminf(d[0] * tb_lo[0], d[0] * tb_hi[0]) + fminf(d[1] * tb_lo[1], d[1] * tb_hi[1]) + fminf(d[2] * tb_lo[2], d[2] * tb_hi[2]);
+                        const float hi_s = fmaxf(d[0] * tb_lo[0], d[0] * tb_hi[0]) + fmaxf(d[1] * tb_lo[1], d[1] * tb_hi[1]) + fmaxf(d[2] * tb_lo[2], d[2] * tb_hi[2]);
+                        const float spad = bpad * (fabsf(d[0]) + fabsf(d[1]) + fabsf(d[2]));
+                        if (fminf(sp_, lo_s) - spad > M->smax[y] || fmaxf(sp_, hi_s) + spad < M->smin[y]) bkeep = 0;
+                    }
+                    if (bkeep) ++a_iter_bf;
+                    if (batch_filter && !bkeep) continue;
+                    for (int l = 0; l < nb; ++l) {
+                        if (cref < 0 && tleaf[l] >= lo && tleaf[l] <= hi) { xref[l] = y; continue; }
+                        if (node_hit(M, y, &ray[l])) {
+                            out[5] += 1;
+                            if (y >= n - 1) cand[l]++;
+                            else stack[128 * l + sp[l]++] = y;
+                        }
+                    }
+                }
+                out[2] += a_iter; out[13] += a_iter_bf;
+                /* phase B */
+                int b_max = 0;
+                for (int l = 0; l < nb; ++l) {
+                    const int stop = cref >= 0 ? cref : (xref[l] >= 0 ? xref[l] : -1);
+                    int cur = n - 1 + tleaf[l], it = 0;
+                    while (cur != stop && M->parent[cur] >= 0) {
+                        const int y = sibling(M, cur);
+                        cur = M->parent[cur];
+                        ++it;
+                        if (node_hit(M, y, &ray[l])) {
+                            if (y >= n - 1) cand[l]++;
+                            else stack[128 * l + sp[l]++] = y;
+                        }
+                    }
+                    out[6] += it;
+                    if (it > b_max) b_max = it;
+                }
+                out[3] += b_max;
+                /* phase C */
+                int c_max = 0, f_max = 0;
+                for (int l = 0; l < nb; ++l) {
+                    int it = 0;
+                    while (sp[l] > 0) {
+                        int node = stack[128 * l + --sp[l]];
+                        for (;;) {
+                            ++it;
+                            const int lc = M->left[node], rc = M->right[node];
+                            const int h0 = node_hit(M, lc, &ray[l]), h1 = node_hit(M, rc, &ray[l]);
+                            if (h0 && lc >= n - 1 && lc - (n - 1) != tleaf[l]) cand[l]++;
+                            if (h1 && rc >= n - 1 && rc - (n - 1) != tleaf[l]) cand[l]++;
+                            const int i0 = h0 && lc < n - 1, i1 = h1 && rc < n - 1;
+                            if (i0 && i1) stack[128 * l + sp[l]++] = rc;
+                            if (i0) node = lc; else if (i1) node = rc; else break;
+                        }
+                    }
+                    out[7] += it; out[8] += cand[l];
+                    if (it > c_max) c_max = it;
+                    if (cand[l] > f_max) f_max = cand[l];
+                }
+                out[4] += c_max; out[9] += f_max;
+            }
+        }
+    }
+    free(list); free(surv); free(stack);
+}

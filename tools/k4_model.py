@@ -1,0 +1,83 @@
+"""CPU model of the trace kernel's traversal: warp-level iteration counts per 32-ray batch for design
+variants (see tools/k4_model.c).  No GPU needed.
+
+    python tools/k4_model.py [grid_n] [rows]
+
+Prints, per variant, the per-batch averages that set K4's instruction count (it is issue-bound):
+phase A / B / C warp iterations, lane-level counts, deferred candidates, and an instruction estimate
+    42*A + 50*B + 100*C + 130*flush + 620   (per-iteration costs from the SASS of the round-1 build,
+                                              fixed part = cull share + compaction + ray set-up + target test)
+to be compared with the measured 104 warp instructions per ray = 3330 per batch (profiles/r01b_kernels_ncu.md).
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fluxpy_b200 import meshes  # noqa: E402  (mesh generators only: pure NumPy)
+
+
+def load():
+    so = '/tmp/libk4model.so'
+    src = os.path.join(ROOT, 'tools', 'k4_model.c')
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(['gcc', '-O2', '-shared', '-fPIC', '-o', so, src, '-lm'])
+    L = ctypes.CDLL(so)
+    vp = ctypes.c_void_p
+    L.k4_build.restype = vp
+    L.k4_build.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
+    L.k4_count.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, vp]
+    L.k4_free.argtypes = [vp]
+    return L
+
+
+def face_geometry(V, F):
+    v0, v1, v2 = (V[F[:, k]].astype(np.float64) for k in range(3))
+    P = (v0 + v1 + v2)/3
+    C = np.cross(v1 - v0, v2 - v0)
+    N = C/np.linalg.norm(C, axis=1)[:, None]
+    return P, N
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 317
+    nrows = int(sys.argv[2]) if len(sys.argv) > 2 else 48
+    V, F = meshes.gaussian_crater(n, 0, dtype=np.float32)
+    P, N = face_geometry(V, F)
+    N[N[:, 2] < 0] *= -1                        # upward normals, as the bench's meshes.upward_normals
+    V = np.ascontiguousarray(V, np.float32)
+    F32 = np.ascontiguousarray(F, np.int32)
+    P, N = np.ascontiguousarray(P), np.ascontiguousarray(N)
+    L = load()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    M = L.k4_build(len(V), p(V), len(F32), p(F32), p(P), p(N))
+    nf = len(F32)
+    rows = np.ascontiguousarray(np.linspace(0, nf - 1, nrows).astype(np.int32))
+    print(f'G({n},0): {nf} faces, {nrows} sample rows x all columns')
+    hdr = ('variant', 'rays/b', 'list', 'A', 'B', 'C', 'A hits', 'B lane', 'C lane', 'cand', 'flush', 'est instr/batch',
+           'instr/ray')
+    print(' | '.join(hdr))
+    for name, chunk, bf, axes in (('chunk 1024 (as built)', 1024, 0, 0), ('chunk 1024 + per-batch filter', 1024, 1, 0),
+                                  ('chunk 1024 + 2 shaft axes', 1024, 0, 1), ('chunk 512', 512, 0, 0),
+                                  ('chunk 512 + 2 shaft axes', 512, 0, 1), ('chunk 256 + 2 shaft axes', 256, 0, 1)):
+        out = np.zeros(16)
+        L.k4_count(M, len(rows), p(rows), chunk, 1e-5, bf, axes, p(out))
+        b = out[0]
+        A, B, C, fl = out[2]/b, out[3]/b, out[4]/b, out[9]/b
+        if bf:
+            A = out[13]/b
+        # the per-batch filter costs ~120 instructions per batch; a unit's list build + cull are shared
+        # by its batches (chunk / 1024 scales how many batches share them)
+        est = 42*A + 50*B + 100*C + 130*fl + 620 + (120 if bf else 0)
+        print(f'{name} | {out[1]/b:.1f} | {out[11]/out[10]:.1f}->{out[12]/out[10]:.1f} | {A:.2f} | {B:.2f} | {C:.2f} | '
+              f'{out[5]/b:.1f} | {out[6]/out[1]:.2f} | {out[7]/out[1]:.2f} | {out[8]/out[1]:.2f} | {fl:.2f} | {est:.0f} | '
+              f'{est/(out[1]/b):.0f}   (units with common ancestor {100*out[15]/out[10]:.0f} %, survivors {100*out[1]/out[14]:.0f} %)')
+    L.k4_free(M)
+
+
+if __name__ == '__main__':
+    main()

@@ -196,6 +196,20 @@ static void node_range(const Model *M, int x, int *lo, int *hi) {
     if (x >= M->n - 1) { *lo = *hi = x - (M->n - 1); }
     else { *lo = M->first[x]; *hi = M->last[x]; }
 }
+static int zone64(const Model *M, int leafnode) { /* largest ancestor (or the leaf) holding at most 64 leaves */
+    int x = leafnode;
+    while (M->parent[x] >= 0) {
+        const int p = M->parent[x];
+        if (M->last[p] - M->first[p] + 1 > 64) break;
+        x = p;
+    }
+    return x;
+}
+static int in_zone(const Model *M, int zone, int leafpos) {
+    int lo, hi;
+    if (zone >= M->n - 1) { lo = hi = zone - (M->n - 1); } else { lo = M->first[zone]; hi = M->last[zone]; }
+    return leafpos >= lo && leafpos <= hi;
+}
 static int sibling(const Model *M, int x) {
     const int p = M->parent[x];
     return M->left[p] == x ? M->right[p] : M->left[p];
@@ -204,7 +218,10 @@ static int sibling(const Model *M, int x) {
 /* out[]: 0 batches, 1 rays, 2 A warp-iterations, 3 B warp-iterations, 4 C warp-iterations, 5 A lane hits,
  * 6 B lane-iterations, 7 C lane-iterations, 8 leaf candidates, 9 flush warp-iterations, 10 units,
  * 11 list length before the filter (sum over units), 12 after the chunk filter, 13 A warp-iterations with
- * the per-batch filter, 14 candidate pairs, 15 units with a usable common ancestor */
+ * the per-batch filter, 14 candidate pairs, 15 units with a usable common ancestor, 16 / 17 phase-C lane visits
+ * rooted in a phase-A / phase-B hit, 18 deferred candidates that are the source triangle itself, 19 / 20
+ * candidates under the 64-leaf ancestor of the source / of the target, 21 phase-A lane hits on records of
+ * at most 64 leaves, 22 phase-B lane hits */
 /* projection of an AABB (lo, hi) on axis a: [*mn, *mx] */
 static void proj_box(const float *lo, const float *hi, const float *a, float *mn, float *mx) {
     *mn = *mx = 0.f;
@@ -214,12 +231,14 @@ static void proj_box(const float *lo, const float *hi, const float *a, float *mn
     }
 }
 
-void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps, int batch_filter, int axes, double *out) {
+void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps, int batch_filter, int axes,
+              int expand_leaves, double *out) {
     const int n = M->n, nchunks = (n + chunk - 1) / chunk;
     int *list = malloc(sizeof(int) * 256), *surv = malloc(sizeof(int) * chunk);
     int *stack = malloc(sizeof(int) * 32 * 128);
     for (int ri = 0; ri < nrows; ++ri) {
         const int i = rows[ri], ileaf = M->face_leaf[i];
+        const int szone = zone64(M, M->n - 1 + ileaf);
         const double *Pi = M->P + 3 * i, *Ni = M->N + 3 * i;
         for (int c = 0; c < nchunks; ++c) {
             const int s0 = c * chunk, s1 = (s0 + chunk < n ? s0 + chunk : n);
@@ -258,9 +277,13 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                 const float pad = 3e-5f * M->scale + 1e-4f * fmaxf(fmaxf(bh[0] - bl[0], bh[1] - bl[1]), bh[2] - bl[2]) + 2e-3f;
                 const float hl[3] = {fminf(px, bl[0]) - pad, fminf(py, bl[1]) - pad, fminf(pz, bl[2]) - pad};
                 const float hh[3] = {fmaxf(px, bh[0]) + pad, fmaxf(py, bh[1]) + pad, fmaxf(pz, bh[2]) + pad};
-                for (int e = 0; e < npath; ++e) {
+                int work[512], nwork = 0;
+                for (int e = npath - 1; e >= 0; --e) {
                     if (cref >= 0 && e == xe) continue;
-                    const int y = list[e]; int lo, hi; node_range(M, y, &lo, &hi);
+                    work[nwork++] = list[e];
+                }
+                while (nwork > 0) {
+                    const int y = work[--nwork]; int lo, hi; node_range(M, y, &lo, &hi);
                     int keep = 1;
                     if (hi < leaf_lo || lo > leaf_hi) {
                         const float *b = M->box + 6 * y, *d = M->sdir + 3 * y;
@@ -295,7 +318,16 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                             }
                         }
                     }
-                    if (keep) sel[nsel++] = y;
+                    if (!keep) continue;
+                    /* variant: a large record that survives is replaced by its two children, which go through
+                     * the filter themselves (the uniform loop is cheaper per record than a phase-C visit and the
+                     * filter works on the smaller boxes) */
+                    if (expand_leaves > 0 && y < n - 1 && hi - lo + 1 > expand_leaves && (hi < leaf_lo || lo > leaf_hi) && nwork < 500 && nsel < 200) {
+                        work[nwork++] = M->right[y];
+                        work[nwork++] = M->left[y];
+                        continue;
+                    }
+                    sel[nsel++] = y;
                 }
             }
             out[12] += nsel;
@@ -350,7 +382,8 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                         if (cref < 0 && tleaf[l] >= lo && tleaf[l] <= hi) { xref[l] = y; continue; }
                         if (node_hit(M, y, &ray[l])) {
                             out[5] += 1;
-                            if (y >= n - 1) cand[l]++;
+                            { int lo2, hi2; node_range(M, y, &lo2, &hi2); if (hi2 - lo2 + 1 <= 64) out[21] += 1; }
+                            if (y >= n - 1) { cand[l]++; const int lp = y - (n - 1); if (lp == ileaf) out[18] += 1; if (in_zone(M, szone, lp)) out[19] += 1; }
                             else stack[128 * l + sp[l]++] = y;
                         }
                     }
@@ -366,8 +399,9 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                         cur = M->parent[cur];
                         ++it;
                         if (node_hit(M, y, &ray[l])) {
-                            if (y >= n - 1) cand[l]++;
-                            else stack[128 * l + sp[l]++] = y;
+                            out[22] += 1;
+                            if (y >= n - 1) { cand[l]++; const int lp = y - (n - 1); if (in_zone(M, szone, lp)) out[19] += 1; if (in_zone(M, zone64(M, n - 1 + tleaf[l]), lp)) out[20] += 1; }
+                            else stack[128 * l + sp[l]++] = y | (1 << 30);
                         }
                     }
                     out[6] += it;
@@ -380,14 +414,17 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                     int it = 0;
                     while (sp[l] > 0) {
                         int node = stack[128 * l + --sp[l]];
+                        const int side = (node >> 30) & 1;
+                        node &= ~(1 << 30);
+                        const int tz = zone64(M, n - 1 + tleaf[l]);
                         for (;;) {
-                            ++it;
+                            ++it; out[16 + side] += 1;
                             const int lc = M->left[node], rc = M->right[node];
                             const int h0 = node_hit(M, lc, &ray[l]), h1 = node_hit(M, rc, &ray[l]);
-                            if (h0 && lc >= n - 1 && lc - (n - 1) != tleaf[l]) cand[l]++;
-                            if (h1 && rc >= n - 1 && rc - (n - 1) != tleaf[l]) cand[l]++;
+                            if (h0 && lc >= n - 1 && lc - (n - 1) != tleaf[l]) { cand[l]++; if (in_zone(M, szone, lc - (n - 1))) out[19] += 1; if (in_zone(M, tz, lc - (n - 1))) out[20] += 1; }
+                            if (h1 && rc >= n - 1 && rc - (n - 1) != tleaf[l]) { cand[l]++; if (in_zone(M, szone, rc - (n - 1))) out[19] += 1; if (in_zone(M, tz, rc - (n - 1))) out[20] += 1; }
                             const int i0 = h0 && lc < n - 1, i1 = h1 && rc < n - 1;
-                            if (i0 && i1) stack[128 * l + sp[l]++] = rc;
+                            if (i0 && i1) stack[128 * l + sp[l]++] = rc | (side << 30);
                             if (i0) node = lc; else if (i1) node = rc; else break;
                         }
                     }

@@ -30,7 +30,7 @@ def load():
     vp = ctypes.c_void_p
     L.k4_build.restype = vp
     L.k4_build.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
-    L.k4_count.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, vp]
+    L.k4_count.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     L.k4_free.argtypes = [vp]
     return L
 
@@ -61,11 +61,15 @@ def main():
     hdr = ('variant', 'rays/b', 'list', 'A', 'B', 'C', 'A hits', 'B lane', 'C lane', 'cand', 'flush', 'est instr/batch',
            'instr/ray')
     print(' | '.join(hdr))
-    for name, chunk, bf, axes in (('chunk 1024 (as built)', 1024, 0, 0), ('chunk 1024 + per-batch filter', 1024, 1, 0),
-                                  ('chunk 1024 + 2 shaft axes', 1024, 0, 1), ('chunk 512', 512, 0, 0),
-                                  ('chunk 512 + 2 shaft axes', 512, 0, 1), ('chunk 256 + 2 shaft axes', 256, 0, 1)):
-        out = np.zeros(16)
-        L.k4_count(M, len(rows), p(rows), chunk, 1e-5, bf, axes, p(out))
+    for name, chunk, bf, axes, expand in (
+            ('chunk 1024 (as built)', 1024, 0, 0, 0), ('chunk 1024 + per-batch filter', 1024, 1, 0, 0),
+            ('chunk 1024 + 2 shaft axes', 1024, 0, 1, 0), ('chunk 512', 512, 0, 0, 0),
+            ('chunk 256 + 2 shaft axes', 256, 0, 1, 0),
+            ('expand records > 16384 leaves', 1024, 0, 0, 16384), ('expand records > 4096 leaves', 1024, 0, 0, 4096),
+            ('expand records > 1024 leaves', 1024, 0, 0, 1024), ('expand records > 256 leaves', 1024, 0, 0, 256),
+            ('expand > 1024 + 2 shaft axes', 1024, 0, 1, 1024)):
+        out = np.zeros(24)
+        L.k4_count(M, len(rows), p(rows), chunk, 1e-5, bf, axes, expand, p(out))
         b = out[0]
         A, B, C, fl = out[2]/b, out[3]/b, out[4]/b, out[9]/b
         if bf:
@@ -76,6 +80,11 @@ def main():
         print(f'{name} | {out[1]/b:.1f} | {out[11]/out[10]:.1f}->{out[12]/out[10]:.1f} | {A:.2f} | {B:.2f} | {C:.2f} | '
               f'{out[5]/b:.1f} | {out[6]/out[1]:.2f} | {out[7]/out[1]:.2f} | {out[8]/out[1]:.2f} | {fl:.2f} | {est:.0f} | '
               f'{est/(out[1]/b):.0f}   (units with common ancestor {100*out[15]/out[10]:.0f} %, survivors {100*out[1]/out[14]:.0f} %)')
+        if name.endswith('(as built)'):
+            r = out[1]
+            print(f'    per ray: phase-A hits {out[5]/r:.2f} ({out[21]/r:.2f} on records of <= 64 leaves), phase-B hits {out[22]/r:.2f}; '
+                  f'phase-C visits rooted in A {out[16]/r:.2f}, in B {out[17]/r:.2f}; deferred candidates {out[8]/r:.2f}: '
+                  f'the source triangle itself {out[18]/r:.2f}, within 64 leaves of the source {out[19]/r:.2f}, of the target {out[20]/r:.2f}')
     L.k4_free(M)
 
 

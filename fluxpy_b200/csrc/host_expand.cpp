@@ -40,10 +40,41 @@ template <class Index> int64_t expand_scalar(const uint32_t *words, int nwords, 
 // 3.3e9 indices/s with ordinary stores against 10e9 with streaming stores.  The row's first entries up
 // to the 64-byte boundary and its last partial group use masked stores, so nothing is ever written
 // outside the row (another thread owns the next one).
-__attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *words, int nwords, int32_t *out,
+// the first `cnt` (<= 16) packed ids with masked stores (head and tail of a row)
+template <bool kWide>
+__attribute__((target("avx512f"), always_inline)) inline void store_masked(char *&dst, __m512i v, int cnt) {
+    if (!kWide) {
+        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << cnt) - 1u), v);
+    } else {
+        const int c0 = cnt < 8 ? cnt : 8, c1 = cnt - c0;
+        _mm512_mask_storeu_epi64(dst, (__mmask8)((1u << c0) - 1u), _mm512_cvtepu32_epi64(_mm512_castsi512_si256(v)));
+        if (c1 > 0)
+            _mm512_mask_storeu_epi64(dst + 64, (__mmask8)((1u << c1) - 1u),
+                                     _mm512_cvtepu32_epi64(_mm512_extracti64x4_epi64(v, 1)));
+    }
+    dst += (size_t)(kWide ? 8 : 4) * cnt;
+}
+// a full group of 16 at a 64-byte aligned dst, streaming
+template <bool kWide>
+__attribute__((target("avx512f"), always_inline)) inline void store_full(char *&dst, __m512i v) {
+    if (!kWide) {
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(dst), v);
+    } else {
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(dst), _mm512_cvtepu32_epi64(_mm512_castsi512_si256(v)));
+        _mm512_stream_si512(reinterpret_cast<__m512i *>(dst + 64), _mm512_cvtepu32_epi64(_mm512_extracti64x4_epi64(v, 1)));
+    }
+    dst += (size_t)(kWide ? 8 : 4) * 16;
+}
+
+// kWide = false: int32 positions, one 64-byte line per 16; kWide = true: int64 positions, the 16 packed
+// ids are zero-extended into two lines of 8.
+template <bool kWide>
+__attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *words, int nwords, void *out_v,
                                                                 int64_t row_entries) {
-    int32_t *dst = out;
-    int head = (int)(((64 - ((uintptr_t)dst & 63)) & 63) / 4); // entries before the first 64-byte boundary
+    constexpr int kBytes = kWide ? 8 : 4;
+    char *dst = reinterpret_cast<char *>(out_v);
+    char *const out = dst;
+    int head = (int)(((64 - ((uintptr_t)dst & 63)) & 63) / kBytes); // entries before the first 64-byte boundary
     if (head > row_entries) head = (int)row_entries;
     const __m512i lanes = _mm512_set_epi32(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
     const __m512i sixteen = _mm512_set1_epi32(16);
@@ -70,8 +101,7 @@ __attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *
                     fill = tot;
                     continue;
                 }
-                _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << head) - 1u), merged);
-                dst += head;
+                store_masked<kWide>(dst, merged, head);
                 alignas(64) int32_t t[32]; // concatenation lanes 0..31; the part after `head` moves to lane 0
                 _mm512_store_si512(t, merged);
                 _mm512_store_si512(t + 16, _mm512_permutexvar_epi32(_mm512_add_epi32(lanes, _mm512_set1_epi32(16 - fill)), v));
@@ -81,8 +111,7 @@ __attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *
                 continue;
             }
             if (tot >= 16) { // dst is 64-byte aligned here and the 16 entries all belong to this row
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(dst), merged);
-                dst += 16;
+                store_full<kWide>(dst, merged);
                 acc = _mm512_permutexvar_epi32(_mm512_add_epi32(lanes, _mm512_set1_epi32(16 - fill)), v);
                 fill = tot - 16;
             } else {
@@ -91,12 +120,9 @@ __attribute__((target("avx512f,popcnt"))) int64_t expand_avx512(const uint32_t *
             }
         }
     }
-    if (fill > 0) {
-        _mm512_mask_storeu_epi32(dst, (__mmask16)((1u << fill) - 1u), acc);
-        dst += fill;
-    }
+    if (fill > 0) store_masked<kWide>(dst, acc, fill);
     _mm_sfence(); // streaming stores are weakly ordered: make them visible before the row is reported done
-    return (int64_t)(dst - out);
+    return (int64_t)(dst - out) / kBytes;
 }
 
 __attribute__((target("popcnt"))) int64_t count_bits_popcnt(const uint32_t *w, int n) {
@@ -135,13 +161,14 @@ int64_t count_bits(const uint32_t *words, int nwords) {
 }
 
 int64_t expand_words(const uint32_t *words, int nwords, int index_width, void *out, int64_t row_entries) {
-    if (index_width == 8) return expand_scalar<int64_t>(words, nwords, reinterpret_cast<int64_t *>(out));
 #if defined(__x86_64__)
     if (have_avx512()) {
         if (row_entries < 0) row_entries = count_bits(words, nwords); // not known: count first
-        return expand_avx512(words, nwords, reinterpret_cast<int32_t *>(out), row_entries);
+        return index_width == 8 ? expand_avx512<true>(words, nwords, out, row_entries)
+                                : expand_avx512<false>(words, nwords, out, row_entries);
     }
 #endif
+    if (index_width == 8) return expand_scalar<int64_t>(words, nwords, reinterpret_cast<int64_t *>(out));
     return expand_scalar<int32_t>(words, nwords, reinterpret_cast<int32_t *>(out));
 }
 

@@ -93,14 +93,15 @@ def test_expand_words_any_alignment_and_no_stray_writes():
             bits = rng.random(nw*32) < dens
             w = np.packbits(bits, bitorder='little').view(np.uint32)
             want = np.flatnonzero(bits)
-            for shift in range(17):
-                buf = np.full(len(want) + 64, -7, np.int32)
-                out = buf[16 + shift:]
-                cnt = ctypes.c_int64(-1)
-                _lib.check(_lib.lib().fluxb200_expand_words(_lib.ptr(w), len(w), 4, out.ctypes.data_as(ctypes.c_void_p),
-                                                            ctypes.byref(cnt)))
-                assert cnt.value == len(want) and np.array_equal(out[:len(want)], want)
-                assert (buf[:16 + shift] == -7).all() and (out[len(want):] == -7).all()
+            for width, dt in ((4, np.int32), (8, np.int64)):
+                for shift in range(17):
+                    buf = np.full(len(want) + 64, -7, dt)
+                    out = buf[16 + shift:]
+                    cnt = ctypes.c_int64(-1)
+                    _lib.check(_lib.lib().fluxb200_expand_words(_lib.ptr(w), len(w), width,
+                                                                out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cnt)))
+                    assert cnt.value == len(want) and np.array_equal(out[:len(want)], want)
+                    assert (buf[:16 + shift] == -7).all() and (out[len(want):] == -7).all()
 
 
 def test_expand_rows_thread_pool():

@@ -196,6 +196,49 @@ static void node_range(const Model *M, int x, int *lo, int *hi) {
     if (x >= M->n - 1) { *lo = *hi = x - (M->n - 1); }
     else { *lo = M->first[x]; *hi = M->last[x]; }
 }
+static double g_margin = 1e-4; /* sine margin of the horizon comparison */
+void k4_set_margin(double m) { g_margin = m; }
+
+static int zone_of(const Model *M, int leafnode, int max_leaves) { /* largest ancestor (or the leaf) with <= max_leaves */
+    int x = leafnode;
+    while (M->parent[x] >= 0) {
+        const int p = M->parent[x];
+        if (M->last[p] - M->first[p] + 1 > max_leaves) break;
+        x = p;
+    }
+    return x;
+}
+
+/* Variant "horizon": hor[f] = upper bound of sin(elevation), measured from the centroid of face f against its
+ * normal, of every point of the OTHER triangles in f's zone (the ancestor of f with at most zone_leaves
+ * leaves).  A ray that leaves f's centroid (or arrives at it) with a larger sine cannot meet any of them.
+ * Sampled densely here (model accuracy); +inf when a zone triangle comes closer than 1e-6 of the scale. */
+void k4_horizons(const Model *M, int zone_leaves, float *hor) {
+    const int n = M->n;
+    for (int f = 0; f < n; ++f) {
+        const int z = zone_of(M, n - 1 + M->face_leaf[f], zone_leaves);
+        int lo, hi;
+        if (z >= n - 1) { lo = hi = z - (n - 1); } else { lo = M->first[z]; hi = M->last[z]; }
+        const double *P = M->P + 3 * f, *N = M->N + 3 * f;
+        double best = -1.0;
+        for (int k = lo; k <= hi; ++k) {
+            const int g = M->leaf_face[k];
+            if (g == f) continue;
+            const float *v[3] = {M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2]};
+            for (int a = 0; a <= 8; ++a)
+                for (int b = 0; a + b <= 8; ++b) {
+                    const double wa = a / 8.0, wb = b / 8.0, wc = 1.0 - wa - wb;
+                    double d[3], l2 = 0, h = 0;
+                    for (int c = 0; c < 3; ++c) { d[c] = wa * v[0][c] + wb * v[1][c] + wc * v[2][c] - P[c]; l2 += d[c] * d[c]; h += d[c] * N[c]; }
+                    const double l = sqrt(l2);
+                    if (l < 1e-6 * M->scale) { best = INFINITY; continue; }
+                    if (h / l > best) best = h / l;
+                }
+        }
+        hor[f] = (float)best;
+    }
+}
+
 static int zone64(const Model *M, int leafnode) { /* largest ancestor (or the leaf) holding at most 64 leaves */
     int x = leafnode;
     while (M->parent[x] >= 0) {
@@ -232,7 +275,7 @@ static void proj_box(const float *lo, const float *hi, const float *a, float *mn
 }
 
 void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps, int batch_filter, int axes,
-              int expand_leaves, double *out) {
+              int expand_leaves, int zone_leaves, const float *hor, double *out) {
     const int n = M->n, nchunks = (n + chunk - 1) / chunk;
     int *list = malloc(sizeof(int) * 256), *surv = malloc(sizeof(int) * chunk);
     int *stack = malloc(sizeof(int) * 32 * 128);
@@ -354,6 +397,25 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                     for (int k = 0; k < 3; ++k) { tb_lo[k] = fminf(tb_lo[k], (float)Pj[k]); tb_hi[k] = fmaxf(tb_hi[k], (float)Pj[k]); }
                 }
                 out[0] += 1; out[1] += nb;
+                /* variant "horizon": the source's near zone is skipped for the whole batch when every ray leaves
+                 * above its horizon; a lane starts the upward walk at the target's zone ancestor when its ray
+                 * arrives above the target's horizon */
+                int src_skip = zone_leaves > 0, tgt_skip[32] = {0};
+                int szlo = 0, szhi = -1;
+                if (zone_leaves > 0) {
+                    const int sz = zone_of(M, n - 1 + ileaf, zone_leaves);
+                    node_range(M, sz, &szlo, &szhi);
+                    for (int l = 0; l < nb; ++l) {
+                        const int j = M->leaf_face[tleaf[l]];
+                        const double *Nj = M->N + 3 * j;
+                        const double es = Ni[0] * ray[l].dx + Ni[1] * ray[l].dy + Ni[2] * ray[l].dz;
+                        const double et = -(Nj[0] * ray[l].dx + Nj[1] * ray[l].dy + Nj[2] * ray[l].dz);
+                        if (!(es > hor[i] + g_margin)) src_skip = 0;
+                        tgt_skip[l] = et > hor[j] + g_margin;
+                        out[23] += tgt_skip[l];
+                    }
+                    out[24] += src_skip;
+                }
                 /* phase A */
                 int sp[32] = {0}, cand[32] = {0}, xref[32];
                 int a_iter = 0, a_iter_bf = 0;
@@ -361,6 +423,7 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                 for (int l = 0; l < nb; ++l) xref[l] = -2;
                 for (int e = 0; e < nsel; ++e) {
                     const int y = sel[e]; int lo, hi; node_range(M, y, &lo, &hi);
+                    if (src_skip && lo >= szlo && hi <= szhi) continue; /* in the source's zone: below every ray */
                     ++a_iter;
                     /* per-batch filter (variant): drop the record for this batch if it is separated from the hull
                      * of the source and the batch's targets along x, y, z or its slab direction */
@@ -394,6 +457,12 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                 for (int l = 0; l < nb; ++l) {
                     const int stop = cref >= 0 ? cref : (xref[l] >= 0 ? xref[l] : -1);
                     int cur = n - 1 + tleaf[l], it = 0;
+                    if (tgt_skip[l] && stop >= 0) { /* start above the target's zone if that is still below `stop` */
+                        const int tz = zone_of(M, cur, zone_leaves);
+                        int zlo, zhi, slo, shi;
+                        node_range(M, tz, &zlo, &zhi); node_range(M, stop, &slo, &shi);
+                        if (tz != stop && slo <= zlo && zhi <= shi) cur = tz;
+                    }
                     while (cur != stop && M->parent[cur] >= 0) {
                         const int y = sibling(M, cur);
                         cur = M->parent[cur];

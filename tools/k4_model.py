@@ -30,8 +30,10 @@ def load():
     vp = ctypes.c_void_p
     L.k4_build.restype = vp
     L.k4_build.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
-    L.k4_count.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    L.k4_count.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+    L.k4_horizons.argtypes = [vp, ctypes.c_int, vp]
     L.k4_free.argtypes = [vp]
+    L.k4_set_margin.argtypes = [ctypes.c_double]
     return L
 
 
@@ -46,9 +48,15 @@ def face_geometry(V, F):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 317
     nrows = int(sys.argv[2]) if len(sys.argv) > 2 else 48
-    V, F = meshes.gaussian_crater(n, 0, dtype=np.float32)
-    P, N = face_geometry(V, F)
-    N[N[:, 2] < 0] *= -1                        # upward normals, as the bench's meshes.upward_normals
+    body = len(sys.argv) > 3 and sys.argv[3] == 'body'
+    if body:                                    # closed, cratered body (BASELINE config 4 stand-in), outward normals
+        V, F = meshes.cratered_body(n, dtype=np.float32)
+        P, N = face_geometry(V, F)
+        N[(N*P).sum(1) < 0] *= -1
+    else:
+        V, F = meshes.gaussian_crater(n, 0, dtype=np.float32)
+        P, N = face_geometry(V, F)
+        N[N[:, 2] < 0] *= -1                    # upward normals, as the bench's meshes.upward_normals
     V = np.ascontiguousarray(V, np.float32)
     F32 = np.ascontiguousarray(F, np.int32)
     P, N = np.ascontiguousarray(P), np.ascontiguousarray(N)
@@ -57,19 +65,28 @@ def main():
     M = L.k4_build(len(V), p(V), len(F32), p(F32), p(P), p(N))
     nf = len(F32)
     rows = np.ascontiguousarray(np.linspace(0, nf - 1, nrows).astype(np.int32))
-    print(f'G({n},0): {nf} faces, {nrows} sample rows x all columns')
+    print(f'{"cratered body" if body else "G"}({n}): {nf} faces, {nrows} sample rows x all columns')
     hdr = ('variant', 'rays/b', 'list', 'A', 'B', 'C', 'A hits', 'B lane', 'C lane', 'cand', 'flush', 'est instr/batch',
            'instr/ray')
     print(' | '.join(hdr))
-    for name, chunk, bf, axes, expand in (
-            ('chunk 1024 (as built)', 1024, 0, 0, 0), ('chunk 1024 + per-batch filter', 1024, 1, 0, 0),
-            ('chunk 1024 + 2 shaft axes', 1024, 0, 1, 0), ('chunk 512', 512, 0, 0, 0),
-            ('chunk 256 + 2 shaft axes', 256, 0, 1, 0),
-            ('expand records > 16384 leaves', 1024, 0, 0, 16384), ('expand records > 4096 leaves', 1024, 0, 0, 4096),
-            ('expand records > 1024 leaves', 1024, 0, 0, 1024), ('expand records > 256 leaves', 1024, 0, 0, 256),
-            ('expand > 1024 + 2 shaft axes', 1024, 0, 1, 1024)):
-        out = np.zeros(24)
-        L.k4_count(M, len(rows), p(rows), chunk, 1e-5, bf, axes, expand, p(out))
+    L.k4_set_margin(float(os.environ.get('K4_MARGIN', '2e-3')))
+    print('horizon margin (sine):', os.environ.get('K4_MARGIN', '2e-3'))
+    hors = {}
+    for zl in (64, 256, 1024, 4096):
+        hors[zl] = np.zeros(nf, np.float32)
+        L.k4_horizons(M, zl, p(hors[zl]))
+        h = hors[zl][np.isfinite(hors[zl])]
+        print(f'horizon of the {zl}-leaf zone: median sin(elev) {np.median(h):.3f}, 90 % {np.quantile(h, 0.9):.3f}, '
+              f'unbounded {100*(1 - len(h)/nf):.1f} %')
+    for name, chunk, bf, axes, expand, zl in (
+            ('chunk 1024 (as built)', 1024, 0, 0, 0, 0), ('chunk 1024 + per-batch filter', 1024, 1, 0, 0, 0),
+            ('chunk 1024 + 2 shaft axes', 1024, 0, 1, 0, 0), ('chunk 512', 512, 0, 0, 0, 0),
+            ('expand records > 4096 leaves', 1024, 0, 0, 4096, 0),
+            ('horizon skip, 64-leaf zones', 1024, 0, 0, 0, 64), ('horizon skip, 256-leaf zones', 1024, 0, 0, 0, 256),
+            ('horizon skip, 1024-leaf zones', 1024, 0, 0, 0, 1024), ('horizon skip, 4096-leaf zones', 1024, 0, 0, 0, 4096),
+            ('horizon 256 + expand > 4096', 1024, 0, 0, 4096, 256)):
+        out = np.zeros(32)
+        L.k4_count(M, len(rows), p(rows), chunk, 1e-5, bf, axes, expand, zl, p(hors[zl]) if zl else None, p(out))
         b = out[0]
         A, B, C, fl = out[2]/b, out[3]/b, out[4]/b, out[9]/b
         if bf:
@@ -80,6 +97,8 @@ def main():
         print(f'{name} | {out[1]/b:.1f} | {out[11]/out[10]:.1f}->{out[12]/out[10]:.1f} | {A:.2f} | {B:.2f} | {C:.2f} | '
               f'{out[5]/b:.1f} | {out[6]/out[1]:.2f} | {out[7]/out[1]:.2f} | {out[8]/out[1]:.2f} | {fl:.2f} | {est:.0f} | '
               f'{est/(out[1]/b):.0f}   (units with common ancestor {100*out[15]/out[10]:.0f} %, survivors {100*out[1]/out[14]:.0f} %)')
+        if zl:
+            print(f'    batches leaving above the source horizon {100*out[24]/b:.0f} %, rays arriving above the target horizon {100*out[23]/out[1]:.0f} %')
         if name.endswith('(as built)'):
             r = out[1]
             print(f'    per ray: phase-A hits {out[5]/r:.2f} ({out[21]/r:.2f} on records of <= 64 leaves), phase-B hits {out[22]/r:.2f}; '

@@ -507,3 +507,199 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
     }
     free(list); free(surv); free(stack);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Exact horizons and a brute-force check of the "horizon skip" (profiles/r01b_k4_model.md): for every
+ * sampled ray that clears the horizon of its source (target) zone, every triangle of that zone is put
+ * through the same float32 Pluecker test the kernel uses; a hit in [0, t_target] would be an occluder the
+ * skip loses.  The ray is set up in float32 exactly as trace.cuh does (compile without FMA contraction).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { float ox, oy, oz, dx, dy, dz; } FRay;
+
+static int pluecker(const FRay *r, float tnear, float tfar, const float *p0, const float *p1, const float *p2, float *t_out) {
+    const float v0x = p0[0] - r->ox, v0y = p0[1] - r->oy, v0z = p0[2] - r->oz;
+    const float v1x = p1[0] - r->ox, v1y = p1[1] - r->oy, v1z = p1[2] - r->oz;
+    const float v2x = p2[0] - r->ox, v2y = p2[1] - r->oy, v2z = p2[2] - r->oz;
+    const float e0x = v2x - v0x, e0y = v2y - v0y, e0z = v2z - v0z;
+    const float e1x = v0x - v1x, e1y = v0y - v1y, e1z = v0z - v1z;
+    const float e2x = v1x - v2x, e2y = v1y - v2y, e2z = v1z - v2z;
+#define MSUB(a, b, c) fmaf((a), (b), -(c))
+#define DOT3(ax, ay, az, bx, by, bz) fmaf((ax), (bx), fmaf((ay), (by), (az) * (bz)))
+    float sx, sy, sz, cx, cy, cz;
+    sx = v2x + v0x; sy = v2y + v0y; sz = v2z + v0z;
+    cx = MSUB(e0y, sz, e0z * sy); cy = MSUB(e0z, sx, e0x * sz); cz = MSUB(e0x, sy, e0y * sx);
+    const float U = DOT3(cx, cy, cz, r->dx, r->dy, r->dz);
+    sx = v0x + v1x; sy = v0y + v1y; sz = v0z + v1z;
+    cx = MSUB(e1y, sz, e1z * sy); cy = MSUB(e1z, sx, e1x * sz); cz = MSUB(e1x, sy, e1y * sx);
+    const float V = DOT3(cx, cy, cz, r->dx, r->dy, r->dz);
+    sx = v1x + v2x; sy = v1y + v2y; sz = v1z + v2z;
+    cx = MSUB(e2y, sz, e2z * sy); cy = MSUB(e2z, sx, e2x * sz); cz = MSUB(e2x, sy, e2y * sx);
+    const float W = DOT3(cx, cy, cz, r->dx, r->dy, r->dz);
+    const float UVW = (U + V) + W;
+    const float eps = 1.1920929e-7f * fabsf(UVW);
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (!(mn >= -eps || mx <= eps)) return 0;
+    const float ab_x = e0z * e1y, ab_y = e0x * e1z, ab_z = e0y * e1x;
+    const float bc_x = e1z * e2y, bc_y = e1x * e2z, bc_z = e1y * e2x;
+    const float cabx = MSUB(e0y, e1z, ab_x), caby = MSUB(e0z, e1x, ab_y), cabz = MSUB(e0x, e1y, ab_z);
+    const float cbcx = MSUB(e1y, e2z, bc_x), cbcy = MSUB(e1z, e2x, bc_y), cbcz = MSUB(e1x, e2y, bc_z);
+    const float Ngx = fabsf(ab_x) < fabsf(bc_x) ? cabx : cbcx;
+    const float Ngy = fabsf(ab_y) < fabsf(bc_y) ? caby : cbcy;
+    const float Ngz = fabsf(ab_z) < fabsf(bc_z) ? cabz : cbcz;
+    const float dn = DOT3(Ngx, Ngy, Ngz, r->dx, r->dy, r->dz), den = dn + dn;
+    const float Tn = DOT3(v0x, v0y, v0z, Ngx, Ngy, Ngz), T = Tn + Tn;
+    if (den == 0.0f) return 0;
+    const float t = T / den;
+    if (!(tnear <= t && t <= tfar)) return 0;
+    *t_out = t;
+    return 1;
+#undef MSUB
+#undef DOT3
+}
+
+/* sup over the triangle (a, b, c) of n.(x - o)/|x - o|, and the smallest |x - o| */
+static void tri_elevation(const double *o, const double *n, const float *a, const float *b, const float *c,
+                          double *sup, double *rmin) {
+    const float *v[3] = {a, b, c};
+    double best = -INFINITY, rm = INFINITY;
+    double q[3][3];
+    for (int k = 0; k < 3; ++k)
+        for (int d = 0; d < 3; ++d) q[k][d] = (double)v[k][d] - o[d];
+    for (int k = 0; k < 3; ++k) { /* vertices and edges */
+        const double *A = q[k], *B = q[(k + 1) % 3];
+        const double la = sqrt(A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+        if (la < rm) rm = la;
+        if (la > 0) { const double e = (n[0] * A[0] + n[1] * A[1] + n[2] * A[2]) / la; if (e > best) best = e; }
+        double E[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
+        /* f(s) = (alpha + beta s) / sqrt(gamma + 2 delta s + eps s^2), s in [0, 1]; stationary point is linear */
+        const double alpha = n[0] * A[0] + n[1] * A[1] + n[2] * A[2], beta = n[0] * E[0] + n[1] * E[1] + n[2] * E[2];
+        const double gamma = la * la, delta = A[0] * E[0] + A[1] * E[1] + A[2] * E[2], eps = E[0] * E[0] + E[1] * E[1] + E[2] * E[2];
+        const double den = beta * delta - alpha * eps;
+        if (den != 0) {
+            const double s = (alpha * delta - beta * gamma) / den;
+            if (s > 0 && s < 1) {
+                const double l2 = gamma + 2 * delta * s + eps * s * s;
+                if (l2 > 0) { const double e = (alpha + beta * s) / sqrt(l2); if (e > best) best = e; }
+            }
+        }
+        /* closest point of the edge to o */
+        if (eps > 0) {
+            double s = -delta / eps; s = s < 0 ? 0 : (s > 1 ? 1 : s);
+            const double l2 = gamma + 2 * delta * s + eps * s * s;
+            if (l2 >= 0 && sqrt(l2) < rm) rm = sqrt(l2);
+        }
+    }
+    /* interior: the ray o + t n (t > 0) pierces the triangle -> elevation 1 there; also the foot of o on the plane */
+    {
+        const double *A = q[0];
+        const double E1[3] = {q[1][0] - A[0], q[1][1] - A[1], q[1][2] - A[2]}, E2[3] = {q[2][0] - A[0], q[2][1] - A[1], q[2][2] - A[2]};
+        const double m[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
+        const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+        if (mm > 0) {
+            const double mA = m[0] * A[0] + m[1] * A[1] + m[2] * A[2];
+            for (int pass = 0; pass < 2; ++pass) { /* pass 0: along n; pass 1: along the plane normal (closest point) */
+                const double *dir = pass ? m : n;
+                const double md = m[0] * dir[0] + m[1] * dir[1] + m[2] * dir[2];
+                if (md == 0) continue;
+                const double t = mA / md;
+                if (!pass && t <= 0) continue;
+                const double X[3] = {t * dir[0] - A[0], t * dir[1] - A[1], t * dir[2] - A[2]};
+                /* barycentric coordinates of X in (E1, E2) */
+                const double d11 = E1[0] * E1[0] + E1[1] * E1[1] + E1[2] * E1[2], d12 = E1[0] * E2[0] + E1[1] * E2[1] + E1[2] * E2[2];
+                const double d22 = E2[0] * E2[0] + E2[1] * E2[1] + E2[2] * E2[2];
+                const double x1 = X[0] * E1[0] + X[1] * E1[1] + X[2] * E1[2], x2 = X[0] * E2[0] + X[1] * E2[1] + X[2] * E2[2];
+                const double det = d11 * d22 - d12 * d12;
+                if (det <= 0) continue;
+                const double u = (x1 * d22 - x2 * d12) / det, w = (x2 * d11 - x1 * d12) / det;
+                if (u >= -1e-9 && w >= -1e-9 && u + w <= 1 + 1e-9) {
+                    if (!pass) best = 1.0;
+                    else { const double l = fabs(t) * sqrt(mm); if (l < rm) rm = l; }
+                }
+            }
+        }
+    }
+    *sup = best; *rmin = rm;
+}
+
+/* hor[f] with the perturbation term: the traced ray is the float32 image of the ideal one (origin and
+ * direction off by a few ulps of the largest coordinate); a point at distance r is displaced by at most
+ * pert / r in the sine.  c_pert in ulps. */
+void k4_horizons_exact(const Model *M, int zone_leaves, double c_pert, float *hor) {
+    const int n = M->n;
+    const double pert = c_pert * 1.1920929e-7 * M->scale;
+    for (int f = 0; f < n; ++f) {
+        const int z = zone_of(M, n - 1 + M->face_leaf[f], zone_leaves);
+        int lo, hi;
+        if (z >= n - 1) { lo = hi = z - (n - 1); } else { lo = M->first[z]; hi = M->last[z]; }
+        double best = -1.0;
+        for (int k = lo; k <= hi; ++k) {
+            const int g = M->leaf_face[k];
+            if (g == f) continue;
+            double sup, rmin;
+            tri_elevation(M->P + 3 * f, M->N + 3 * f, M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2], &sup, &rmin);
+            /* the ray starts 1e-3 along itself: a zone point can be that much closer to the origin than to p_f */
+            const double r = rmin - 1.0e-3 * 1.001;
+            const double e = r > pert ? sup + pert / r : INFINITY;
+            if (e > best) best = e;
+        }
+        hor[f] = (float)best;
+        if ((double)hor[f] < best) hor[f] = nextafterf(hor[f], INFINITY);
+    }
+}
+
+/* out: 0 rays, 1 rays clearing the source horizon, 2 clearing the target horizon, 3 VIOLATIONS at the source
+ * end (a zone triangle hit in [0, t_target]), 4 violations at the target end, 5 Pluecker tests done,
+ * 6 rays that miss their own target */
+void k4_check_horizon(const Model *M, int nrows, const int *rows, int zone_leaves, const float *hor, double eps, double *out) {
+    const int n = M->n;
+    for (int ri = 0; ri < nrows; ++ri) {
+        const int i = rows[ri];
+        const double *Pi = M->P + 3 * i, *Ni = M->N + 3 * i;
+        const int sz = zone_of(M, n - 1 + M->face_leaf[i], zone_leaves);
+        int slo, shi; node_range(M, sz, &slo, &shi);
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double *Pj = M->P + 3 * j, *Nj = M->N + 3 * j;
+            const double ddx = Pj[0] - Pi[0], ddy = Pj[1] - Pi[1], ddz = Pj[2] - Pi[2];
+            double a = Ni[0] * ddx + Ni[1] * ddy + Ni[2] * ddz, b = -(Nj[0] * ddx + Nj[1] * ddy + Nj[2] * ddz);
+            a = a > 0 ? a : 0; b = b > 0 ? b : 0;
+            if (!((float)(a * b) > (float)eps)) continue;
+            /* setup_ray<float> of trace.cuh */
+            const float pix = (float)Pi[0], piy = (float)Pi[1], piz = (float)Pi[2];
+            const float fdx = (float)Pj[0] - pix, fdy = (float)Pj[1] - piy, fdz = (float)Pj[2] - piz;
+            const float nrm = sqrtf((fdx * fdx + fdy * fdy) + fdz * fdz);
+            const float feps = 1e-3f;
+            if (!(nrm > feps)) continue;
+            FRay r;
+            r.dx = fdx / nrm; r.dy = fdy / nrm; r.dz = fdz / nrm;
+            r.ox = pix + feps * r.dx; r.oy = piy + feps * r.dy; r.oz = piz + feps * r.dz;
+            float tj;
+            const float *t0 = M->V + 3 * M->F[3 * j], *t1 = M->V + 3 * M->F[3 * j + 1], *t2 = M->V + 3 * M->F[3 * j + 2];
+            out[0] += 1;
+            if (!pluecker(&r, 0.f, INFINITY, t0, t1, t2, &tj)) { out[6] += 1; continue; }
+            const double es = Ni[0] * r.dx + Ni[1] * r.dy + Ni[2] * r.dz, et = -(Nj[0] * r.dx + Nj[1] * r.dy + Nj[2] * r.dz);
+            if (es > hor[i]) {
+                out[1] += 1;
+                for (int k = slo; k <= shi; ++k) {
+                    const int g = M->leaf_face[k];
+                    if (g == i || g == j) continue;
+                    float t;
+                    out[5] += 1;
+                    if (pluecker(&r, 0.f, tj, M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2], &t)) out[3] += 1;
+                }
+            }
+            if (et > hor[j]) {
+                out[2] += 1;
+                const int tz = zone_of(M, n - 1 + M->face_leaf[j], zone_leaves);
+                int tlo, thi; node_range(M, tz, &tlo, &thi);
+                for (int k = tlo; k <= thi; ++k) {
+                    const int g = M->leaf_face[k];
+                    if (g == j || g == i) continue;
+                    float t;
+                    out[5] += 1;
+                    if (pluecker(&r, 0.f, tj, M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2], &t)) out[4] += 1;
+                }
+            }
+        }
+    }
+}

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument('--grid', type=int, default=GRID_N, help='Gaussian-crater grid size n')
     ap.add_argument('--cpu-rows', type=int, default=0, help='rows of the CPU sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--option', action='append', default=[], metavar='NAME=VALUE',
+                    help='library option (fluxb200_set_option), e.g. horizon_skip=1; recorded in config.options')
     return ap.parse_args()
 
 
@@ -217,6 +219,11 @@ def main():
     nf = F.shape[0]
     fluxpy_b200.CudaTrimeshShapeModel.device = local_rank
     sm = fluxpy_b200.CudaTrimeshShapeModel(V, F, N)
+    options = {}
+    for item in args.option:
+        name, _, value = item.partition('=')
+        sm.set_option(name, int(value))
+        options[name] = int(value)
     stream = torch.cuda.ExternalStream(sm.cuda_stream(), device=dev)
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     info = sm.bvh_info()
@@ -378,7 +385,8 @@ def main():
                        'rows_per_step_per_gpu': args.rows, 'parallelism': f'row-slabs x{world}',
                        'l2': 'explicit 256 MB flush between steps + each step streams >3 GB of CSR output',
                        'bvh': {'nodes': info.num_nodes, 'top_nodes_smem': info.num_top_nodes,
-                               'depth': info.max_depth, 'build_ms': info.ms_build}},
+                               'depth': info.max_depth, 'build_ms': info.ms_build},
+                       'options': options, 'trace_counters': sm.trace_counters()},
             'pairs_all_per_s': pairs_all/(ms_dev_max/1e3),
             'nnz_per_step': nnz_all/steps,
             'csr_assembly_s_full_matrix_est': full_est,

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 OVERFLOW = 2
 
 #: every symbol include/fluxb200.h declares
@@ -29,7 +29,7 @@ EXPORTS = (
     'fluxb200_csr_extract', 'fluxb200_csr_matmat',
     'fluxb200_visibility', 'fluxb200_is_occluded', 'fluxb200_intersect1',
     'fluxb200_visibility_bruteforce', 'fluxb200_slab_plan', 'fluxb200_mesh_stream',
-    'fluxb200_set_option', 'fluxb200_expand_words', 'fluxb200_expand_rows',
+    'fluxb200_set_option', 'fluxb200_expand_words', 'fluxb200_expand_rows', 'fluxb200_trace_counters',
 )
 
 
@@ -115,6 +115,7 @@ def lib():
     L.fluxb200_slab_plan.argtypes = [sz, i32, vp, vp]
     L.fluxb200_mesh_stream.argtypes = [vp, pp]
     L.fluxb200_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    L.fluxb200_trace_counters.argtypes = [vp, vp]
     L.fluxb200_expand_words.argtypes = [vp, sz, i32, vp, ctypes.POINTER(i64)]
     L.fluxb200_expand_rows.argtypes = [vp, sz, sz, vp, i32, vp, i32]
     for name in EXPORTS:

@@ -67,33 +67,49 @@ template <class T> struct TraceArgs {
     int ninternal, ntop, nfaces;
     uint32_t *bits;                 // m x nwords visibility words, sorted-column order
     uint32_t *row_counts;           // m
-    unsigned long long *tested;     // [0] rays traced, [1] work-unit counter of this launch
+    unsigned long long *tested;     // [0] rays traced, [1] work-unit counter of this launch; kHor: [2] batches,
+                                    // [3] batches walked without the zone records, [4] rays whose walk started at the zone node
     int *error_flag;
     float scale;                    // largest |coordinate| of the mesh (pads of the shaft filter)
     int shaft_filter;               // 0: test every record of the per-unit list (A/B check)
+    // horizon skip (kHor instantiation only; horizon.cuh) -- appended, so the layout above is unchanged
+    const float2 *hz;               // per face: (hor, rmin) from the current P, N
+    const int *zone_node;           // per leaf: its zone's node (-1: the leaf alone)
+    const float4 *colH;             // per sorted column: (hor, rmin, zone node, up code of the zone node)
+    int zone_leaves;                // Z
+    float pert;                     // ray perturbation + Pluecker slack, in length units
 };
 
 // explicit shared-space loads / stores from a 32-bit shared address kept in a register: the
 // generic-pointer form makes ptxas rebuild the address (thread id, cluster CTA id, window base)
 // inside the hot loops
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+#ifndef FB_EMU
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ float4 lds_f4(smem_addr_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int2 lds_i2(uint32_t addr) {
+__device__ __forceinline__ int2 lds_i2(smem_addr_t addr) {
     int2 v;
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ int lds_i1(uint32_t addr) {
+__device__ __forceinline__ int lds_i1(smem_addr_t addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts_i1(uint32_t addr, int v) {
+__device__ __forceinline__ void sts_i1(smem_addr_t addr, int v) {
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+#else // host build of the kernels for the SIMT emulator (tools/simt, test infrastructure): plain pointers
+typedef size_t smem_addr_t;
+inline float4 lds_f4(smem_addr_t addr) { return *reinterpret_cast<const float4 *>(addr); }
+inline int2 lds_i2(smem_addr_t addr) { return *reinterpret_cast<const int2 *>(addr); }
+inline int lds_i1(smem_addr_t addr) { return *reinterpret_cast<const volatile int *>(addr); }
+inline void sts_i1(smem_addr_t addr, int v) { *reinterpret_cast<volatile int *>(addr) = v; }
+#endif
 
 constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 #ifndef FB_TRACE_MIN_BLOCKS
@@ -122,8 +138,12 @@ constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 // kTop = true is the plain variant (top of the tree staged in shared memory,
 // top-down traversal from the root only); it is kept as the measured
 // alternative and as an independent check of the path walk.
-template <class T, bool kTop>
+// kHor = true adds the horizon skip (horizon.cuh): a batch whose rays all leave above the source
+// face's near-zone horizon walks the list without the records inside zone(i); a ray that arrives
+// above its target's horizon starts the upward walk at zone(j)'s node instead of the target leaf.
+template <class T, bool kTop, bool kHor = false>
 __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kernel(const TraceArgs<T> A) {
+    static_assert(!(kTop && kHor), "the horizon skip belongs to the path-walk variant");
     extern __shared__ float4 smem_top[];
     __shared__ uint32_t words_s[kTraceWarps][32];
     __shared__ int leaf_s[kLeafCap][kTraceThreads];
@@ -135,12 +155,13 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
         __syncthreads();
     }
     const BvhView bvh{A.nodes, smem_top, A.tri, kTop ? A.ntop : 0, A.ninternal, A.nfaces, A.error_flag};
-    uint32_t path_base = (uint32_t)__cvta_generic_to_shared(&path_s[warp][0]);
-    uint32_t range_base = (uint32_t)__cvta_generic_to_shared(&range_s[warp][0]);
-    uint32_t leaf_base = (uint32_t)__cvta_generic_to_shared(&leaf_s[0][tid]);
+    smem_addr_t path_base = (smem_addr_t)__cvta_generic_to_shared(&path_s[warp][0]);
+    smem_addr_t range_base = (smem_addr_t)__cvta_generic_to_shared(&range_s[warp][0]);
+    smem_addr_t leaf_base = (smem_addr_t)__cvta_generic_to_shared(&leaf_s[0][tid]);
     asm volatile("" : "+r"(path_base), "+r"(range_base), "+r"(leaf_base)); // keep them: do not rematerialise
     const unsigned total_units = (unsigned)A.m * (unsigned)A.nchunks;
     unsigned long long tested = 0;
+    unsigned hc_batches = 0, hc_src = 0, hc_tgt = 0; // kHor counters (lane 0 / per lane)
 
     while (true) {
         unsigned unit = 0;
@@ -220,6 +241,29 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 __syncwarp();
             }
         }
+        // horizon skip, per unit: leaf range of zone(i), the source face's horizon, and whether the
+        // upward walk of this unit's rays may start at the target's zone node (the walk's end C must
+        // lie above every zone: a node of more than Z leaves)
+        int zlo = 0, zhi = -1, nout = 0;
+        float hor_i = INFINITY;
+        bool tskip_unit = false;
+        if constexpr (kHor) {
+            if (A.ninternal > 0) {
+                const int ileaf = A.face_leaf[i];
+                const int zn = A.zone_node[ileaf];
+                zlo = zhi = ileaf;
+                if (zn >= 0) {
+                    const int2 zr = A.node_range[zn];
+                    zlo = zr.x;
+                    zhi = zr.y;
+                }
+                hor_i = __ldg(A.hz + i).x;
+                if (cref != -0x7fffffff) {
+                    const int2 cr = A.node_range[cref];
+                    tskip_unit = cr.y - cr.x + 1 > A.zone_leaves;
+                }
+            }
+        }
         // ---- phase 1: cull -----------------------------------------------------
         uint32_t myword = 0;
         float bl0 = INFINITY, bl1 = INFINITY, bl2 = INFINITY, bh0 = -INFINITY, bh1 = -INFINITY, bh2 = -INFINITY;
@@ -269,6 +313,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
             float4 ra[2], rb2[2], rc[2];
             int2 rr[2];
             bool keepr[2], other[2];
+            bool inzone[2] = {false, false}; // kHor: a kept record inside zone(i), other than the source's own
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int e = h * 32 + lane;
@@ -290,6 +335,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     if (e != xdrop) {
                         keepr[h] = keep;
                         other[h] = !keep;
+                        if constexpr (kHor) inzone[h] = keep && e != 0 && rg.x >= zlo && rg.y <= zhi;
                     }
                 }
             }
@@ -298,11 +344,22 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
             const uint32_t lt = (1u << lane) - 1u;
             nsel = __popc(kb0) + __popc(kb1);
             nall = nsel + __popc(ob0) + __popc(ob1);
+            uint32_t zb0 = 0, zb1 = 0;
+            if constexpr (kHor) { // three classes: [kept, outside zone(i)] [kept, inside] [not kept]
+                zb0 = __ballot_sync(0xffffffffu, inzone[0]);
+                zb1 = __ballot_sync(0xffffffffu, inzone[1]);
+                nout = nsel - __popc(zb0) - __popc(zb1);
+            }
             __syncwarp(); // every lane holds its two records: the list can be rewritten
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 int d = -1;
-                if (keepr[h]) d = (h ? __popc(kb0) : 0) + __popc((h ? kb1 : kb0) & lt);
+                if constexpr (kHor) {
+                    const uint32_t k0 = kb0 & ~zb0, k1 = kb1 & ~zb1;
+                    if (inzone[h]) d = nout + (h ? __popc(zb0) : 0) + __popc((h ? zb1 : zb0) & lt);
+                    else if (keepr[h]) d = (h ? __popc(k0) : 0) + __popc((h ? k1 : k0) & lt);
+                    else if (other[h]) d = nsel + (h ? __popc(ob0) : 0) + __popc((h ? ob1 : ob0) & lt);
+                } else if (keepr[h]) d = (h ? __popc(kb0) : 0) + __popc((h ? kb1 : kb0) & lt);
                 else if (other[h]) d = nsel + (h ? __popc(ob0) : 0) + __popc((h ? ob1 : ob0) & lt);
                 if (d >= 0) {
                     path_s[warp][3 * d] = ra[h];
@@ -340,9 +397,12 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
             int bit = 0, tleaf = -1, tface = 0;
             float tj = 0.f;
             bool active = false, blocked = false, overshoot = false;
+            int scol = 0;       // kHor: my column and the centroid distance of my ray
+            float dist_h = 0.f;
             if (want < total) {
                 bit = __fns(wk, 0, (int)(want - before) + 1);
                 const int s = s0 + k * 32 + bit;
+                if constexpr (kHor) scol = s;
                 const Real4<T> Pj = load_real4<T>(A.colP + s);
                 if (setup_ray(Pi, Pj, ray)) { // else masked pair: "vis by default" (shape.py:392)
                     tleaf = A.col_leaf[s];
@@ -354,7 +414,11 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                         // past the centroid: such a batch uses the unfiltered list.
                         const float ex = (float)Pj.x - (float)Pi.x, ey = (float)Pj.y - (float)Pi.y,
                                     ez = (float)Pj.z - (float)Pi.z;
-                        overshoot = tj * 1.000002f > sqrtf(ex * ex + ey * ey + ez * ez) + (1e-5f * A.scale + 1e-3f);
+                        if constexpr (kHor) {
+                            dist_h = sqrtf(ex * ex + ey * ey + ez * ez);
+                            overshoot = tj * 1.000002f > dist_h + (1e-5f * A.scale + 1e-3f);
+                        } else
+                            overshoot = tj * 1.000002f > sqrtf(ex * ex + ey * ey + ez * ez) + (1e-5f * A.scale + 1e-3f);
                     } else {
                         blocked = true; // the ray misses its own target: closest hit is not j
                     }
@@ -388,10 +452,24 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 // covered by phase B.
                 int xref = ~tleaf;
                 const bool fullpath = __any_sync(0xffffffffu, active && overshoot);
-                const int nuse = fullpath ? nall : nsel;
+                int nuse = fullpath ? nall : nsel;
+                if constexpr (kHor) {
+                    // source end: every ray of the batch leaves above the horizon of zone(i) -> no triangle of
+                    // the zone other than i can be met: the records inside the zone are not walked
+                    bool clear = true; // a lane without a ray does not object
+                    if (active) {
+                        const float si = (float)Ni.x * ray.dx + (float)Ni.y * ray.dy + (float)Ni.z * ray.dz;
+                        clear = si > hor_i;
+                    }
+                    if (__all_sync(0xffffffffu, clear) && !fullpath) {
+                        nuse = nout;
+                        ++hc_src;
+                    }
+                    ++hc_batches;
+                }
                 const float tmax_a = active ? tmax : -1.0f; // a lane without a ray never hits
                 if (cref != -0x7fffffff) { // X is not in the list: nothing to check per record
-                    uint32_t addr = path_base;
+                    smem_addr_t addr = path_base;
                     for (int ks = 0; ks < nuse; ++ks, addr += 48) {
                         const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
                         if (child_hit(ray, rb, a, b, cc, tmax_a)) {
@@ -401,7 +479,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                         }
                     }
                 } else { // the chunk straddles several records: every lane skips the one holding its target
-                    uint32_t addr = path_base, raddr = range_base;
+                    smem_addr_t addr = path_base, raddr = range_base;
                     for (int ks = 0; ks < nuse; ++ks, addr += 48, raddr += 8) {
                         const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
                         const int2 rg = lds_i2(raddr);
@@ -420,6 +498,23 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 // sibling is record code ^ 1 of the node array.
                 const int stop = cref != -0x7fffffff ? cref : xref;
                 int cur = ~tleaf, code = tleaf >= 0 ? A.leaf_up[tleaf] : -1;
+                if constexpr (kHor) {
+                    // target end: the ray arrives above the horizon of zone(j) and the tested interval does
+                    // not run on past p_j as far as the zone's nearest other triangle -> nothing in zone(j)
+                    // except j can be met: the walk starts at the zone's node
+                    if (active && tskip_unit) {
+                        const float4 h = __ldg(A.colH + scol);
+                        const Real4<T> Nj = load_real4<T>(A.colN + scol);
+                        const float st = -((float)Nj.x * ray.dx + (float)Nj.y * ray.dy + (float)Nj.z * ray.dz);
+                        const float beyond = tmax - (dist_h - ray_eps()); // ideal hit: dist - 1e-3 along the ray
+                        const int zn = __float_as_int(h.z);
+                        if (zn >= 0 && st > h.x && beyond + A.pert < h.y) {
+                            cur = zn;
+                            code = __float_as_int(h.w);
+                            ++hc_tgt;
+                        }
+                    }
+                }
                 while (active && cur != stop && code >= 0) {
                     const float4 *rec = A.nodes + 3 * (size_t)(unsigned)(code ^ 1);
                     const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
@@ -475,6 +570,15 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
         __syncwarp();
     }
     if (lane == 0 && tested) atomicAdd(A.tested, tested);
+    if constexpr (kHor) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) hc_tgt += __shfl_xor_sync(0xffffffffu, hc_tgt, o);
+        if (lane == 0) {
+            atomicAdd(A.tested + 2, (unsigned long long)hc_batches);
+            atomicAdd(A.tested + 3, (unsigned long long)hc_src);
+            atomicAdd(A.tested + 4, (unsigned long long)hc_tgt);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -744,24 +848,32 @@ __global__ void col_gather_kernel(const uint32_t *__restrict__ pos, const int *_
     rank_of_pos[q] = s;
 }
 
-// interleave host-side P (nf x 3), N (nf x 3), A (nf) into the packed arrays
+// interleave host-side P (nf x 3), N (nf x 3), A (nf) into the packed arrays; *changed is set when a
+// P or N value differs from the one it replaces (the horizons of horizon.cuh depend on them)
 template <class T>
 __global__ void pack_face_kernel(const T *__restrict__ P, const T *__restrict__ N, const T *__restrict__ A,
-                                 int nf, Real4<T> *__restrict__ faceP, Real4<T> *__restrict__ faceN) {
+                                 int nf, Real4<T> *__restrict__ faceP, Real4<T> *__restrict__ faceN,
+                                 int *__restrict__ changed) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
+    bool diff = false;
     if (P) {
-        faceP[f].x = P[3 * (size_t)f];
-        faceP[f].y = P[3 * (size_t)f + 1];
-        faceP[f].z = P[3 * (size_t)f + 2];
+        const T x = P[3 * (size_t)f], y = P[3 * (size_t)f + 1], z = P[3 * (size_t)f + 2];
+        diff = !(faceP[f].x == x && faceP[f].y == y && faceP[f].z == z); // NaN counts as a change
+        faceP[f].x = x;
+        faceP[f].y = y;
+        faceP[f].z = z;
     }
     if (A) faceP[f].w = A[f];
     if (N) {
-        faceN[f].x = N[3 * (size_t)f];
-        faceN[f].y = N[3 * (size_t)f + 1];
-        faceN[f].z = N[3 * (size_t)f + 2];
+        const T x = N[3 * (size_t)f], y = N[3 * (size_t)f + 1], z = N[3 * (size_t)f + 2];
+        diff = diff || !(faceN[f].x == x && faceN[f].y == y && faceN[f].z == z);
+        faceN[f].x = x;
+        faceN[f].y = y;
+        faceN[f].z = z;
         faceN[f].w = (T)0;
     }
+    if (diff) *changed = 1;
 }
 
 template <class T>

@@ -15,6 +15,7 @@
 #include "prims.cuh"
 #include "spmv.cuh"
 #include "blockops.cuh"
+#include "horizon.cuh"
 #include "trace.cuh"
 #include "host_expand.h"
 
@@ -43,6 +44,12 @@ struct fluxb200_mesh {
     int slab_limit_opt = 1 << 30;
     int blocks_per_sm = 4;
     int shaft_filter_opt = 1;
+    // horizon skip of the trace kernel (horizon.cuh).  Off by default: validated bit for bit against the
+    // oracle on the SIMT emulator (tools/simt) but not yet measured on a B200.
+    int horizon_skip_opt = 0;
+    int horizon_zone_opt = 256; // Z: leaves per near zone
+    bool hz_dirty = true;       // P, N or the tree changed since the horizons were computed
+    DevBuf hz, zone_node, zone_up, colH;
     float ms_build = 0.f;
     float scene_h[7] = {};
 
@@ -236,6 +243,13 @@ void bvh_build(fluxb200_mesh *M) {
                                                            M->first.as<int>(), M->last.as<int>(),
                                                            M->node_range.as<int2>());
     }
+    M->hz_dirty = true;
+    if (M->horizon_skip_opt) {
+        M->zone_node.reserve(sizeof(int) * n);
+        M->zone_up.reserve(sizeof(int) * n);
+        zone_kernel<<<G, B, 0, st>>>(n, M->leaf_up.as<int>(), M->node_up.as<int>(), M->node_range.as<int2>(),
+                                     M->horizon_zone_opt, M->zone_node.as<int>(), M->zone_up.as<int>());
+    }
     FB_CUDA(cudaGetLastError());
     FB_CUDA(cudaEventRecord(M->ev[1], st));
     int h[2];
@@ -274,11 +288,17 @@ template <class T> void set_face_data(fluxb200_mesh *M, const void *P, const voi
     if (P) FB_CUDA(cudaMemcpyAsync(dP, P, sizeof(T) * 3 * nf, cudaMemcpyHostToDevice, st));
     if (N) FB_CUDA(cudaMemcpyAsync(dN, N, sizeof(T) * 3 * nf, cudaMemcpyHostToDevice, st));
     if (A) FB_CUDA(cudaMemcpyAsync(dA, A, sizeof(T) * nf, cudaMemcpyHostToDevice, st));
+    int *changed = M->scalars.as<int>() + 7; // scalars: [0] ntop, [1] depth, [6] traversal error flag, [7] this
+    FB_CUDA(cudaMemsetAsync(changed, 0, sizeof(int), st));
     pack_face_kernel<T><<<blocks_for((int64_t)nf, 256), 256, 0, st>>>(
         P ? dP : nullptr, N ? dN : nullptr, A ? dA : nullptr, (int)nf, M->faceP.as<Real4<T>>(),
-        M->faceN.as<Real4<T>>());
+        M->faceN.as<Real4<T>>(), changed);
     FB_CUDA(cudaGetLastError());
+    int h_changed = 1;
+    if (M->horizon_skip_opt) // the horizons are recomputed only when P or N really changed
+        FB_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
+    if (h_changed) M->hz_dirty = true;
 }
 
 template <class T> void get_face_data(fluxb200_mesh *M, void *P, void *N, void *A) {
@@ -308,6 +328,10 @@ void upload_index_sets(fluxb200_mesh *M, const int64_t *I, size_t m, const int64
 
 // ---- per-call pieces shared by the two-phase and the streaming assembly ---------
 
+// what a float32 ray can be off the ideal one, plus the slack of the Pluecker edge tests: 16 ulps of the
+// largest coordinate (tools/k4_horizon_check.py)
+inline float horizon_pert(const fluxb200_mesh *M) { return 16.0f * 1.1920929e-7f * M->scene_h[6]; }
+
 // index sets -> device; columns sorted by leaf (Morton) position and gathered
 template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n,
                                     double eps) {
@@ -322,8 +346,8 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
     int launches = 0;
     upload_index_sets(M, I, m, J, n);
     M->stats.h2d_bytes = (int64_t)(sizeof(int) * (m + n));
-    M->tested.reserve(sizeof(unsigned long long) * 2);
-    FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 2, st));
+    M->tested.reserve(sizeof(unsigned long long) * 8); // [0] rays, [1] work-unit counter, [2..4] horizon-skip counters
+    FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 8, st));
     if (m && n) {
         M->ckeys.reserve(sizeof(uint64_t) * n);
         M->cvals.reserve(sizeof(uint32_t) * n);
@@ -348,6 +372,24 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
             M->rank_of_pos.as<int>());
         FB_CUDA(cudaGetLastError());
         launches += 2 + (M->sorter.launches - l0);
+        if (M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0) {
+            const int nf = (int)M->nf;
+            if (M->hz_dirty) { // from the shape model's CURRENT P, N
+                M->hz.reserve(sizeof(float2) * (size_t)nf);
+                horizon_kernel<T><<<blocks_for((int64_t)nf * 32, 256), 256, 0, st>>>(
+                    nf, M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->face_leaf.as<int>(),
+                    M->zone_node.as<int>(), M->node_range.as<int2>(), M->tri.as<float4>(), horizon_pert(M),
+                    M->hz.as<float2>());
+                M->hz_dirty = false;
+                ++launches;
+            }
+            M->colH.reserve(sizeof(float4) * n);
+            col_horizon_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(
+                M->col_face.as<int>(), M->col_leaf.as<int>(), (int)n, M->hz.as<float2>(), M->zone_node.as<int>(),
+                M->zone_up.as<int>(), M->colH.as<float4>());
+            FB_CUDA(cudaGetLastError());
+            ++launches;
+        }
     }
     return launches;
 }
@@ -382,6 +424,12 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.error_flag = M->scalars.as<int>() + 6;
     A.scale = M->scene_h[6];
     A.shaft_filter = M->shaft_filter_opt;
+    const bool hor = M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0;
+    A.hz = hor ? M->hz.as<float2>() : nullptr;
+    A.zone_node = hor ? M->zone_node.as<int>() : nullptr;
+    A.colH = hor ? M->colH.as<float4>() : nullptr;
+    A.zone_leaves = M->horizon_zone_opt;
+    A.pert = horizon_pert(M);
     A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
@@ -394,6 +442,7 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     const int grid = (int)std::min<int64_t>((int64_t)M->num_sms * M->blocks_per_sm,
                                             std::max<int64_t>(1, ceil_div(units, kTraceWarps)));
     if (M->ntop > 0) trace_kernel<T, true><<<grid, kTraceThreads, smem, st>>>(A);
+    else if (hor) trace_kernel<T, false, true><<<grid, kTraceThreads, 0, st>>>(A);
     else trace_kernel<T, false><<<grid, kTraceThreads, 0, st>>>(A);
     FB_CUDA(cudaGetLastError());
 }
@@ -997,7 +1046,8 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
                           &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->node_range, &M->rows,
                           &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
                           &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
-                          &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout, &M->jbits};
+                          &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout, &M->jbits,
+                          &M->hz, &M->zone_node, &M->zone_up, &M->colH};
         for (DevBuf *b : bufs) b->release();
         for (int k = 0; k < fluxb200_mesh::kSlots; ++k) {
             M->sbits[k].release(); M->scounts[k].release(); M->scounts64[k].release(); M->sindptr[k].release();
@@ -1495,6 +1545,22 @@ int fluxb200_mesh_stream(fluxb200_mesh *M, void **stream) {
     });
 }
 
+int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[4]) {
+    return guarded([&] {
+        FB_REQUIRE(M && out, "NULL argument");
+        DeviceGuard guard(M->device);
+        unsigned long long h[8] = {};
+        if (M->tested.p) {
+            FB_CUDA(cudaMemcpyAsync(h, M->tested.p, sizeof(h), cudaMemcpyDeviceToHost, M->stream));
+            FB_CUDA(cudaStreamSynchronize(M->stream));
+        }
+        out[0] = (int64_t)h[0];
+        out[1] = (int64_t)h[2];
+        out[2] = (int64_t)h[3];
+        out[3] = (int64_t)h[4];
+    });
+}
+
 int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
     return guarded([&] {
         FB_REQUIRE(M && name, "NULL argument");
@@ -1507,6 +1573,15 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             bvh_build(M);
         } else if (s == "shaft_filter") {
             M->shaft_filter_opt = value ? 1 : 0;
+        } else if (s == "horizon_skip") {
+            M->horizon_skip_opt = value ? 1 : 0;
+            M->have_count = false;
+            bvh_build(M); // the zone table belongs to the tree
+        } else if (s == "horizon_zone") {
+            FB_REQUIRE(value >= 1 && value <= 1023, "horizon_zone out of range (1..1023 leaves)");
+            M->horizon_zone_opt = (int)value;
+            M->have_count = false;
+            bvh_build(M);
         } else if (s == "blocks_per_sm") {
             FB_REQUIRE(value >= 1 && value <= 8, "blocks_per_sm out of range");
             M->blocks_per_sm = (int)value;

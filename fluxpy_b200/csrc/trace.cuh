@@ -158,7 +158,11 @@ __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const 
     const float no = fmaf(c.x, r.ox, fmaf(c.y, r.oy, c.z * r.oz));
     const float nd = fmaf(c.x, r.dx, fmaf(c.y, r.dy, c.z * r.dz));
     float rn; // approximate reciprocal (MUFU.RCP): +-inf when the ray runs parallel to the slab
+#ifndef FB_EMU
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nd));
+#else
+    rn = 1.0f / nd; // SIMT-emulator build (tools/simt); the box / slab test only has to be conservative
+#endif
     const float s0 = (b.w - no) * rn, s1 = (c.w - no) * rn;
     // parallel ray: (b.w-no), (c.w-no) of opposite sign -> (-inf, +inf), no clipping;
     // same sign -> both +inf or both -inf -> empty.  NaN (0*inf) is dropped by fmin/fmax.

@@ -348,6 +348,13 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
     def set_option(self, name, value):
         _lib.check(_lib.lib().fluxb200_set_option(self._handle, name.encode(), int(value)))
 
+    def trace_counters(self):
+        """Counters of the last assembly's trace launches (``fluxb200_trace_counters``)."""
+        out = np.zeros(4, np.int64)
+        _lib.check(_lib.lib().fluxb200_trace_counters(self._handle, _lib.ptr(out)))
+        return dict(rays=int(out[0]), batches=int(out[1]), batches_source_skip=int(out[2]),
+                    rays_target_skip=int(out[3]))
+
     def cuda_stream(self):
         s = ctypes.c_void_p()
         _lib.check(_lib.lib().fluxb200_mesh_stream(self._handle, ctypes.byref(s)))

@@ -34,7 +34,7 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 5
+#define FLUXB200_ABI_VERSION 6
 
 #define FLUXB200_OK 0
 #define FLUXB200_ERROR 1
@@ -234,8 +234,15 @@ int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
  * "sub_rows" (rows per sub-slab of fluxb200_ff_assemble), "fill_rows" (rows per CTA of the
  * CSR fill's un-permute kernel: 0 = as many as fit in shared memory, -1 = no shared memory),
  * "host_expand" (1: fluxb200_ff_assemble ships visibility words to the host and host threads
- * write the column indices; 0: the indices themselves are copied), "host_threads" (0 = automatic). */
+ * write the column indices; 0: the indices themselves are copied), "host_threads" (0 = automatic),
+ * "horizon_skip" (1: the trace kernel skips a face's near zone for rays that clear its horizon --
+ * exact, see csrc/horizon.cuh; default 0 until it has been measured on a B200), "horizon_zone"
+ * (leaves per near zone, 1..1023, default 256). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
+/* Counters of the last assembly's trace launches: out[0] rays traced (= stats.pairs_tested), and with
+ * "horizon_skip" on: out[1] 32-ray batches, out[2] batches walked without the records of the source
+ * face's near zone, out[3] rays whose upward walk started at the target's zone node. */
+int fluxb200_trace_counters(fluxb200_mesh *mesh, int64_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,28 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    if os.environ.get('FLUXB200_TEST_EMU') == '1':
+        # Test infrastructure only: run the gpu-marked tests against the library's own CUDA sources
+        # compiled for the host on the SIMT emulator (tools/simt).  The package itself has no such
+        # switch -- the emulated library is swapped in from here, from the test side.
+        sys.path.insert(0, os.path.join(ROOT, 'tools', 'simt'))
+        import build_emu
+        from fluxpy_b200 import _lib
+        _lib.SO_PATH = build_emu.build()
+        _lib._lib = None
+    zone = os.environ.get('FLUXB200_TEST_HORIZON')
+    if zone:
+        # Run whatever is selected with the trace kernel's horizon skip switched on for every shape model
+        # (value = leaves per near zone): the whole gpu tier then doubles as the check of that variant,
+        # on the emulator and on a B200 alike.
+        from fluxpy_b200 import shape
+        plain_init = shape.CudaTrimeshShapeModel.__init__
+
+        def init_with_horizon(self, *args, **kwargs):
+            plain_init(self, *args, **kwargs)
+            self.set_option('horizon_zone', int(zone))
+            self.set_option('horizon_skip', 1)
+        shape.CudaTrimeshShapeModel.__init__ = init_with_horizon
 
 
 @pytest.fixture(scope='session')

@@ -274,14 +274,45 @@ inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
     return cudaSuccess;
 }
 inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = -1; return cudaSuccess; }
+// Device allocations carry a 256-byte red zone on either side (checked when the block is freed: a kernel
+// that wrote out of bounds aborts the process with a message) and start out poisoned, not zeroed.
+namespace emu {
+constexpr size_t kRedZone = 256;
+constexpr unsigned char kRedByte = 0xA5;
+struct AllocHeader {
+    size_t bytes;
+    uint64_t magic;
+};
+inline void check_redzones(void *user) {
+    unsigned char *base = static_cast<unsigned char *>(user) - kRedZone;
+    AllocHeader h;
+    memcpy(&h, base, sizeof(h));
+    if (h.magic != 0xFB200E5Dull) fail("cudaFree of a pointer cudaMalloc did not return (or its header was overwritten)");
+    for (size_t k = sizeof(h); k < kRedZone; ++k)
+        if (base[k] != kRedByte) fail("out-of-bounds write BELOW a device allocation");
+    const unsigned char *tail = static_cast<unsigned char *>(user) + h.bytes;
+    for (size_t k = 0; k < kRedZone; ++k)
+        if (tail[k] != kRedByte) fail("out-of-bounds write ABOVE a device allocation");
+}
+} // namespace emu
 inline cudaError_t cudaMalloc(void **p, size_t bytes) {
-    // device memory is uninitialised: poison it so that code relying on zeros shows up
-    *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
-    if (!*p) return cudaErrorMemoryAllocation;
-    memset(*p, 0xCD, bytes);
+    const size_t total = (bytes + 2 * emu::kRedZone + 255) / 256 * 256;
+    unsigned char *base = static_cast<unsigned char *>(aligned_alloc(256, total));
+    if (!base) return cudaErrorMemoryAllocation;
+    memset(base, emu::kRedByte, emu::kRedZone);
+    const emu::AllocHeader h{bytes, 0xFB200E5Dull};
+    memcpy(base, &h, sizeof(h));
+    memset(base + emu::kRedZone, 0xCD, bytes); // device memory is uninitialised: code relying on zeros shows up
+    memset(base + emu::kRedZone + bytes, emu::kRedByte, emu::kRedZone);
+    *p = base + emu::kRedZone;
     return cudaSuccess;
 }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) {
+    if (!p) return cudaSuccess;
+    emu::check_redzones(p);
+    free(static_cast<unsigned char *>(p) - emu::kRedZone);
+    return cudaSuccess;
+}
 inline cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) {
     *p = aligned_alloc(256, (bytes + 255) / 256 * 256);
     return *p ? cudaSuccess : cudaErrorMemoryAllocation;

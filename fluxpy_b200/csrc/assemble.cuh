@@ -111,6 +111,21 @@ inline int lds_i1(smem_addr_t addr) { return *reinterpret_cast<const volatile in
 inline void sts_i1(smem_addr_t addr, int v) { *reinterpret_cast<volatile int *>(addr) = v; }
 #endif
 
+// Loop-iteration counters of the trace kernel, SIMT-emulator builds only (tools/simt): the kernel is bound by
+// instruction issue, so these counts (per 32-ray batch) are what a variant is judged by before GPU time
+// is spent on it.  [0] batches, [1] phase-A iterations, [2] / [3] phase-B / phase-C iterations of the
+// slowest lane, [4] converged exact-test iterations, [5] / [6] phase-B / phase-C lane-iterations.
+#ifdef FB_EMU
+namespace emu_stats {
+inline unsigned long long iters[8];
+inline int warp_max(int v) {
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+} // namespace emu_stats
+#define FB_COUNT(k, v) __atomic_fetch_add(&emu_stats::iters[k], (unsigned long long)(v), __ATOMIC_RELAXED)
+#endif
+
 constexpr int kLeafCap = 8; // deferred candidate triangles per lane
 #ifndef FB_TRACE_MIN_BLOCKS
 #define FB_TRACE_MIN_BLOCKS 4 // resident CTAs per SM the register budget is cut for (64 registers)
@@ -467,6 +482,10 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     }
                     ++hc_batches;
                 }
+#ifdef FB_EMU
+                if (lane == 0) FB_COUNT(0, 1), FB_COUNT(1, nuse);
+                int emu_nb = 0;
+#endif
                 const float tmax_a = active ? tmax : -1.0f; // a lane without a ray never hits
                 if (cref != -0x7fffffff) { // X is not in the list: nothing to check per record
                     smem_addr_t addr = path_base;
@@ -520,6 +539,9 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
                     cur = code >> 1;
                     code = A.node_up[cur];
+#ifdef FB_EMU
+                    ++emu_nb;
+#endif
                     if (child_hit(ray, rb, a, b, cc, tmax)) {
                         const int ref = __float_as_int(a.w);
                         if (ref < 0) push_leaf(~ref);
@@ -531,8 +553,21 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     if (sp > 0) node = stack[--sp];
                     else active = false;
                 }
+#ifdef FB_EMU
+                {
+                    FB_COUNT(5, emu_nb);
+                    const int mb = emu_stats::warp_max(emu_nb);
+                    if (lane == 0) FB_COUNT(2, mb);
+                }
+#endif
             }
+#ifdef FB_EMU
+            int emu_c = 0;
+#endif
             while (active) {
+#ifdef FB_EMU
+                ++emu_c;
+#endif
                 float4 q[6];
                 load_node<kTop>(bvh, node, q);
                 const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
@@ -548,10 +583,20 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     else active = false;
                 }
             }
+#ifdef FB_EMU
+            if (!kTop) {
+                FB_COUNT(6, emu_c);
+                const int mc = emu_stats::warp_max(emu_c);
+                if (lane == 0) FB_COUNT(3, mc);
+            }
+#endif
             { // converged exact tests of the listed candidates
                 int mx = nl;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#ifdef FB_EMU
+                if (lane == 0) FB_COUNT(4, mx);
+#endif
                 for (int q = 0; q < mx; ++q)
                     if (q < nl && !blocked)
                         blocked = leaf_occludes(bvh, ray, tj, lds_i1(leaf_base + (uint32_t)q * (uint32_t)(sizeof(int) * kTraceThreads)), tface);

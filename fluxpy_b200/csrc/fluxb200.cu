@@ -1561,6 +1561,14 @@ int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[4]) {
     });
 }
 
+#ifdef FB_EMU
+// SIMT-emulator builds only (tools/simt): read and reset the trace kernel's loop-iteration counters
+int fluxb200_emu_trace_iterations(int64_t out[8]) {
+    for (int k = 0; k < 8; ++k) out[k] = (int64_t)__atomic_exchange_n(&emu_stats::iters[k], 0ull, __ATOMIC_RELAXED);
+    return 0;
+}
+#endif
+
 int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
     return guarded([&] {
         FB_REQUIRE(M && name, "NULL argument");

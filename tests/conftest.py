@@ -36,6 +36,25 @@ def pytest_configure(config):
         shape.CudaTrimeshShapeModel.__init__ = init_with_horizon
 
 
+# gpu-tier tests that hand torch CUDA tensors (device pointers) to the library or need NCCL: no emulator run
+NEEDS_REAL_DEVICE = ('test_device_resident_radiosity_and_steady_state', 'test_block_extraction_and_lowrank_feed',
+                     'test_two_rank_sharded_assembly_and_solve')
+# too large for the emulator's ~2 M rays/s (full 50k / 82k / 200k-face matrices)
+TOO_LARGE_FOR_EMU = ('test_closed_cratered_body_82k_sampled_rows', 'test_full_50k_matrix_properties',
+                     'test_slab_properties_at_full_size', 'test_culling_structures_are_conservative_at_scale')
+
+
+def pytest_collection_modifyitems(config, items):
+    if os.environ.get('FLUXB200_TEST_EMU') != '1':
+        return
+    for item in items:
+        name = item.originalname if hasattr(item, 'originalname') else item.name
+        if name in NEEDS_REAL_DEVICE:
+            item.add_marker(pytest.mark.skip(reason='needs a real CUDA device (torch tensors / NCCL)'))
+        elif name in TOO_LARGE_FOR_EMU and os.environ.get('FLUXB200_TEST_EMU_LARGE') != '1':
+            item.add_marker(pytest.mark.skip(reason='too large for the SIMT emulator (FLUXB200_TEST_EMU_LARGE=1 to run)'))
+
+
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN

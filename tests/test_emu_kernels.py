@@ -21,7 +21,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # the quick part of the gpu tier (seconds each on the emulator); the rest runs there with
-#   FLUXB200_TEST_EMU=1 python -m pytest tests -m gpu -k "not 82k and not full_50k and not full_size and not device_resident"
+#   FLUXB200_TEST_EMU=1 python -m pytest tests -m gpu      (conftest skips what needs a real device or is too large)
 SUBSET = ('test_sphere_fixtures or test_sphere_shape_api or (test_crater_vs_oracle_and_golden and not case2) '
           'or test_steady_state_temperature or test_edge_cases or test_fill_kernel_variants_agree '
           'or test_coincident_faces_tie_rule or test_ingersoll_bowl or test_random_triangle_soup')

@@ -47,7 +47,7 @@ struct fluxb200_mesh {
     // horizon skip of the trace kernel (horizon.cuh).  Off by default: validated bit for bit against the
     // oracle on the SIMT emulator (tools/simt) but not yet measured on a B200.
     int horizon_skip_opt = 0;
-    int horizon_zone_opt = 256; // Z: leaves per near zone
+    int horizon_zone_opt = 1023; // Z: leaves per near zone (below the 1024-column chunk: the upward walk must end above every zone)
     bool hz_dirty = true;       // P, N or the tree changed since the horizons were computed
     DevBuf hz, zone_node, zone_up, colH;
     float ms_build = 0.f;
@@ -1586,7 +1586,7 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->have_count = false;
             bvh_build(M); // the zone table belongs to the tree
         } else if (s == "horizon_zone") {
-            FB_REQUIRE(value >= 1 && value <= 1023, "horizon_zone out of range (1..1023 leaves)");
+            FB_REQUIRE(value >= 1 && value <= 65536, "horizon_zone out of range (1..65536 leaves)");
             M->horizon_zone_opt = (int)value;
             M->have_count = false;
             bvh_build(M);

@@ -237,7 +237,7 @@ int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
  * write the column indices; 0: the indices themselves are copied), "host_threads" (0 = automatic),
  * "horizon_skip" (1: the trace kernel skips a face's near zone for rays that clear its horizon --
  * exact, see csrc/horizon.cuh; default 0 until it has been measured on a B200), "horizon_zone"
- * (leaves per near zone, 1..1023, default 256). */
+ * (leaves per near zone, default 1023; the target end of the skip needs zones below the 1024-column chunk). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 /* Counters of the last assembly's trace launches: out[0] rays traced (= stats.pairs_tested), and with
  * "horizon_skip" on: out[1] 32-ray batches, out[2] batches walked without the records of the source

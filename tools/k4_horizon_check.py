@@ -2,7 +2,7 @@
 sampled ray that clears a horizon is Pluecker-tested (float32, as the kernel does) against every triangle
 of the zone it would skip.  Any hit is a violation.  CPU only.
 
-    python tools/k4_horizon_check.py [grid_n] [rows] [zone_leaves] [c_pert] [scale]
+    python tools/k4_horizon_check.py [grid_n] [rows] [zone_leaves] [c_pert] [scale] [formula]
 """
 import ctypes
 import os
@@ -23,6 +23,7 @@ def main():
     zone = int(sys.argv[3]) if len(sys.argv) > 3 else 256
     c_pert = float(sys.argv[4]) if len(sys.argv) > 4 else 16.0
     scale = float(sys.argv[5]) if len(sys.argv) > 5 else 1.0
+    formula = int(sys.argv[6]) if len(sys.argv) > 6 else 1
     so = '/tmp/libk4model_chk.so'
     src = os.path.join(ROOT, 'tools', 'k4_model.c')
     subprocess.check_call(['gcc', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-o', so, src, '-lm'])
@@ -44,6 +45,7 @@ def main():
     M = L.k4_build(len(V), p(V), len(F32), p(F32), p(P), p(N))
     nf = len(F32)
     hor = np.zeros(nf, np.float32)
+    L.k4_set_formula(formula)
     L.k4_horizons_exact(M, zone, c_pert, p(hor))
     fin = hor[np.isfinite(hor)]
     print(f'G({n},0) x {scale}: {nf} faces, zone {zone} leaves, perturbation {c_pert} ulp: horizon median {np.median(fin):.4f}, '

@@ -624,6 +624,8 @@ static void tri_elevation(const double *o, const double *n, const float *a, cons
 /* hor[f] with the perturbation term: the traced ray is the float32 image of the ideal one (origin and
  * direction off by a few ulps of the largest coordinate); a point at distance r is displaced by at most
  * pert / r in the sine.  c_pert in ulps. */
+static int g_formula = 0; /* 0: r = rmin - 1e-3 (first version); 1: r = max(rmin, 0.9e-3), twice the perturbation */
+void k4_set_formula(int f) { g_formula = f; }
 void k4_horizons_exact(const Model *M, int zone_leaves, double c_pert, float *hor) {
     const int n = M->n;
     const double pert = c_pert * 1.1920929e-7 * M->scale;
@@ -637,9 +639,17 @@ void k4_horizons_exact(const Model *M, int zone_leaves, double c_pert, float *ho
             if (g == f) continue;
             double sup, rmin;
             tri_elevation(M->P + 3 * f, M->N + 3 * f, M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2], &sup, &rmin);
-            /* the ray starts 1e-3 along itself: a zone point can be that much closer to the origin than to p_f */
-            const double r = rmin - 1.0e-3 * 1.001;
-            const double e = r > pert ? sup + pert / r : INFINITY;
+            double r, e;
+            if (g_formula == 0) {
+                /* the ray starts 1e-3 along itself: a zone point can be that much closer to the origin than to p_f */
+                r = rmin - 1.0e-3 * 1.001;
+                e = r > pert ? sup + pert / r : INFINITY;
+            } else {
+                /* a point of the ray with t >= 0 is at least 1e-3 from p_f, a point of the triangle at least rmin:
+                 * the two unit directions differ by at most 2 delta / max(rmin, 1e-3) */
+                r = fmax(rmin, 0.9e-3);
+                e = sup + 2.0 * pert / r;
+            }
             if (e > best) best = e;
         }
         hor[f] = (float)best;

@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                         const float st = -((float)Nj.x * ray.dx + (float)Nj.y * ray.dy + (float)Nj.z * ray.dz);
                         const float beyond = tmax - (dist_h - ray_eps()); // ideal hit: dist - 1e-3 along the ray
                         const int zn = __float_as_int(h.z);
-                        if (zn >= 0 && st > h.x && beyond + A.pert < h.y) {
+                        if (zn >= 0 && st > h.x && beyond + 2.0f * A.pert < h.y) {
                             cur = zn;
                             code = __float_as_int(h.w);
                             ++hc_tgt;

@@ -116,9 +116,11 @@ __device__ __forceinline__ void triangle_elevation(const double p[3], const doub
 }
 
 // One warp per face.  hz[f] = (hor, rmin).  pert = the displacement (in length units) a float32 ray can have
-// against the ideal one plus the slack of the Pluecker edge tests: a point at distance r moves by at most
-// pert / r in the direction seen from p_f.  The ray starts 1e-3 along itself (shape.py:380), so a zone point
-// can be that much closer to the ray's origin than to p_f: r = rmin - 1e-3.
+// against the ideal one plus the slack of the Pluecker edge tests.  If the traced ray meets triangle g, a point
+// x of g lies within pert of a point y of the ideal ray; the unit directions of x and y seen from p_f differ
+// by at most 2 pert / max(|x - p_f|, |y - p_f|) <= 2 pert / rmin(g), at either end of the ray.  So a ray
+// whose n_f.d exceeds  sup_g + 2 pert |n_f| / rmin(g)  for every g of the zone meets none of them
+// (checked by brute force: tools/k4_horizon_check.py, formula 1).
 template <class T>
 __global__ void __launch_bounds__(256)
     horizon_kernel(int nf, const Real4<T> *__restrict__ faceP, const Real4<T> *__restrict__ faceN,
@@ -145,8 +147,7 @@ __global__ void __launch_bounds__(256)
         double sup, rm;
         triangle_elevation(p, n, __ldg(tri + 3 * (size_t)k), __ldg(tri + 3 * (size_t)k + 1),
                            __ldg(tri + 3 * (size_t)k + 2), sup, rm);
-        const double r = rm - 1.001e-3;
-        const double e = r > (double)pert ? sup + (double)pert * nlen / r : INFINITY;
+        const double e = rm > 0.0 ? sup + 2.0 * (double)pert * nlen / rm : INFINITY;
         best = (e > best || e != e) ? e : best;
         rzone = fmin(rzone, rm);
     }

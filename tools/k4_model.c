@@ -624,7 +624,7 @@ static void tri_elevation(const double *o, const double *n, const float *a, cons
 /* hor[f] with the perturbation term: the traced ray is the float32 image of the ideal one (origin and
  * direction off by a few ulps of the largest coordinate); a point at distance r is displaced by at most
  * pert / r in the sine.  c_pert in ulps. */
-static int g_formula = 0; /* 0: r = rmin - 1e-3 (first version); 1: r = max(rmin, 0.9e-3), twice the perturbation */
+static int g_formula = 0; /* 0: r = rmin - 1e-3 (first version); 1: r = rmin, twice the perturbation */
 void k4_set_formula(int f) { g_formula = f; }
 void k4_horizons_exact(const Model *M, int zone_leaves, double c_pert, float *hor) {
     const int n = M->n;
@@ -645,10 +645,10 @@ void k4_horizons_exact(const Model *M, int zone_leaves, double c_pert, float *ho
                 r = rmin - 1.0e-3 * 1.001;
                 e = r > pert ? sup + pert / r : INFINITY;
             } else {
-                /* a point of the ray with t >= 0 is at least 1e-3 from p_f, a point of the triangle at least rmin:
-                 * the two unit directions differ by at most 2 delta / max(rmin, 1e-3) */
-                r = fmax(rmin, 0.9e-3);
-                e = sup + 2.0 * pert / r;
+                /* a point x of the triangle within delta of a point y of the ray: the unit directions from p_f
+                 * differ by at most 2 delta / max(|x - p_f|, |y - p_f|) <= 2 delta / rmin (either end of the ray) */
+                r = rmin;
+                e = r > 0 ? sup + 2.0 * pert / r : INFINITY;
             }
             if (e > best) best = e;
         }

@@ -117,3 +117,12 @@ def test_horizon_skip_is_exact_and_exercised(emu_lib):
     assert res[1]['batches_source_skip'] > 0.5 * res[1]['batches'], res[1]
     assert res[1]['rays_target_skip'] > 0.3 * res[1]['rays'], res[1]
     assert res[0]['batches_source_skip'] > 0 and res[0]['rays_target_skip'] > 0, res[0]
+
+
+def test_fuzz_kernels_against_the_oracle(emu_lib):
+    """A short run of tools/simt/fuzz.py: random small meshes (soups, degenerate and coincident triangles,
+    sheets, fans, closed bodies, translated and rescaled coordinates, user-supplied normals), random index
+    sets, both dtypes, horizon skip off and on -- every CSR bit-identical to the oracle's."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'simt', 'fuzz.py'), '25', '500000'],
+                         cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and 'fuzz ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

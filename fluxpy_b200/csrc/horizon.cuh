@@ -88,6 +88,8 @@ __device__ __forceinline__ void triangle_elevation(const double p[3], const doub
     const double E2[3] = {q[2][0] - A[0], q[2][1] - A[1], q[2][2] - A[2]};
     const double m[3] = {E1[1] * E2[2] - E1[2] * E2[1], E1[2] * E2[0] - E1[0] * E2[2], E1[0] * E2[1] - E1[1] * E2[0]};
     const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+    if (degenerate_triangle((float)E1[0], (float)E1[1], (float)E1[2], (float)E2[0], (float)E2[1], (float)E2[2]))
+        best = INFINITY; // no well-defined plane: the exact test's hits on it obey no geometry (lbvh.cuh)
     if (mm > 0.0) {
         const double mA = m[0] * A[0] + m[1] * A[1] + m[2] * A[2];
         const double d11 = E1[0] * E1[0] + E1[1] * E1[1] + E1[2] * E1[2];

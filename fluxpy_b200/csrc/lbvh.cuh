@@ -156,6 +156,19 @@ __global__ void morton_kernel(const float *__restrict__ V32, const int *__restri
     vals[f] = (uint32_t)f;
 }
 
+// A triangle whose two edge vectors are (numerically) parallel -- collinear vertices, a repeated vertex, a
+// zero-length edge.  The per-triangle Pluecker test of the arithmetic contract has no well-defined plane for
+// it: its edge functions are rounding noise and the "hit" distance it reports is unrelated to where the
+// triangle is, so no bounding volume is conservative for it.  Such leaves get the whole scene as their box and
+// an open slab (every ray reaches them and the exact test decides, as in the contract's brute force), and a
+// near zone that holds one has no horizon (horizon.cuh).  sin(angle between the edges) <= 1e-4.
+__device__ __forceinline__ bool degenerate_triangle(float e1x, float e1y, float e1z, float e2x, float e2y, float e2z) {
+    const float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+    const float nn = nx * nx + ny * ny + nz * nz;
+    const float l1 = e1x * e1x + e1y * e1y + e1z * e1z, l2 = e2x * e2x + e2y * e2y + e2z * e2z;
+    return !(nn > 1e-8f * l1 * l2);
+}
+
 // ---- K3: Karras (2012) hierarchy ---------------------------------------------
 // node ids: internal i in [0, n-2] (root = 0), leaf k -> (n-1) + k
 __device__ __forceinline__ int lbvh_delta(const uint64_t *__restrict__ keys, int n, int i, int j) {
@@ -228,6 +241,15 @@ __global__ void refit_kernel(const float *__restrict__ V32, const int *__restric
     b[6] = e1y * e2z - e1z * e2y; // area normal (2 * area * unit normal)
     b[7] = e1z * e2x - e1x * e2z;
     b[8] = e1x * e2y - e1y * e2x;
+    if (degenerate_triangle(e1x, e1y, e1z, e2x, e2y, e2z)) { // never culled: the exact test decides
+        const float big = 2.0f * ord_flt(scene[6]) + 1.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            b[c] = -big;
+            b[3 + c] = big;
+            b[6 + c] = 0.f;
+        }
+    }
     int node = (n - 1) + k;
 #pragma unroll
     for (int c = 0; c < 9; ++c) box[9 * (size_t)node + c] = b[c];
@@ -281,6 +303,14 @@ __global__ void slab_extent_kernel(int n, const float4 *__restrict__ tri, const 
     if (k >= n) return;
     const float4 p0 = tri[3 * (size_t)k], p1 = tri[3 * (size_t)k + 1], p2 = tri[3 * (size_t)k + 2];
     int x = (n - 1) + k;
+    if (degenerate_triangle(p1.x - p0.x, p1.y - p0.y, p1.z - p0.z, p2.x - p0.x, p2.y - p0.y, p2.z - p0.z)) {
+        while (x >= 0) { // open slab for the leaf and every ancestor
+            atomicMin(&slab[2 * (size_t)x], flt_ord(-FLT_MAX));
+            atomicMax(&slab[2 * (size_t)x + 1], flt_ord(FLT_MAX));
+            x = parent[x];
+        }
+        return;
+    }
     while (x >= 0) {
         if (x < n - 1 && last[x] - first[x] + 1 > limit) break; // ancestors only get larger
         const float *b = box + 9 * (size_t)x;

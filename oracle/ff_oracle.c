@@ -162,7 +162,26 @@ static void closest_hit_brute(const oracle_scene *s, const float org[3], const f
 
 /* --- acceleration: median-split BVH with a double-precision slab test ------ */
 
+/* A triangle whose edge vectors are numerically parallel (collinear vertices, a repeated vertex) has no
+ * well-defined plane: the Pluecker test's edge functions are rounding noise and the distance it reports is
+ * unrelated to where the triangle is, so no box is conservative for it.  The brute force is the definition;
+ * the accelerator never culls such a triangle (found by tools/simt/fuzz.py). */
+static int tri_degenerate(const float *p) {
+    const float e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    const float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    const float l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2], l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+    return !(nn > 1e-8f * l1 * l2);
+}
+
 static void tri_bounds(const float *p, float lo[3], float hi[3]) {
+    if (tri_degenerate(p)) {
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = -FLT_MAX / 4;
+            hi[k] = FLT_MAX / 4;
+        }
+        return;
+    }
     for (int k = 0; k < 3; ++k) {
         lo[k] = fminf(fminf(p[k], p[3 + k]), p[6 + k]);
         hi[k] = fmaxf(fmaxf(p[k], p[3 + k]), p[6 + k]);

@@ -335,3 +335,46 @@ def test_block_extraction_and_lowrank_feed(mods):
     assert err <= 1.05*np.linalg.svd(Bh.toarray(), compute_uv=False)[k] + 1e-12
     out = lowrank.estimate_rank(B, 1e-2)
     assert out is not None and 1 <= out[1].size <= min(Bh.shape) and out[1][-1] >= 1e-2*out[1][0]
+
+
+def test_degenerate_triangles_follow_the_brute_force_definition(mods):
+    """Collinear / repeated-vertex triangles have no well-defined plane: the per-triangle Pluecker test
+    answers with rounding noise and a hit distance unrelated to where the triangle is, so no bounding volume
+    is conservative for them.  The LBVH gives such leaves the whole scene as box and an open slab (and their
+    near zone no horizon), so the tree still returns what the contract's brute force returns.  Found by
+    tools/simt/fuzz.py (seeds 100493, 101531)."""
+    rng = np.random.default_rng(5)
+    V, F = mods['meshes'].gaussian_crater(14, 3, dtype=np.float32)
+    V = V.astype(np.float64)
+    extra_V, extra_F = [], []
+    nv = len(V)
+    for k in range(6):
+        a, b = V[rng.integers(0, nv)] + [0, 0, 0.05], V[rng.integers(0, nv)] + [0, 0, 0.3]
+        if k % 3 == 0:
+            tri = [a, b, 0.5*(a + b)]                    # collinear
+        elif k % 3 == 1:
+            tri = [a, a, b]                              # zero-length edge
+        else:
+            tri = [a, b, a + 0.25*(b - a)]               # collinear, uneven
+        extra_F.append([nv + len(extra_V) + q for q in range(3)])
+        extra_V.extend(tri)
+    V = np.concatenate([V, np.array(extra_V)]).astype(np.float32)
+    F = np.concatenate([F, np.array(extra_F)])
+    F = np.concatenate([F, [[F[0, 0], F[0, 0], F[0, 1]]]])          # repeated vertex index
+    for dtype in (np.float32, np.float64):
+        Vd = V.astype(dtype)
+        N = mods['meshes'].upward_normals(Vd, F)
+        N[~np.isfinite(N).all(1)] = [0, 0, 1]
+        sm = mods['shape'].CudaTrimeshShapeModel(Vd, F, N.copy())
+        brute = mods['oracle'].OracleShapeModel(Vd, F, N=N.copy(), use_bvh=False)
+        tree = mods['oracle'].OracleShapeModel(Vd, F, N=N.copy(), use_bvh=True)
+        for eps in (1e-5, -1.0):
+            FF = mods['ff'].get_form_factor_matrix(sm, eps=eps)
+            assert same_csr(FF, mods['oracle'].get_form_factor_matrix(brute, eps=eps))
+            assert same_csr(FF, mods['oracle'].get_form_factor_matrix(tree, eps=eps))
+        I = np.arange(sm.num_faces)
+        vis = sm._get_visibility(I, I)
+        assert (vis == sm._get_visibility(I, I, _bruteforce=True)).all()
+        vo = brute.get_visibility_matrix()
+        vo[I, I] = False
+        assert (vis == vo).all()

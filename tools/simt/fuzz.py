@@ -21,7 +21,7 @@ sys.path.insert(0, HERE)
 
 
 def random_mesh(rng):
-    kind = rng.integers(0, 7)
+    kind = rng.integers(0, 8)
     dtype = np.float32 if rng.random() < 0.6 else np.float64
     scale = float(rng.choice([1.0, 1.0, 1e-2, 37.0, 4.0e3]))
     if kind == 0:      # tiny soup
@@ -71,6 +71,11 @@ def random_mesh(rng):
         rim = np.stack([np.cos(ang), np.sin(ang), rng.normal(scale=0.3, size=nt + 1)], 1)
         V = np.concatenate([[[0, 0, float(rng.normal(scale=0.5))]], rim])
         F = np.stack([np.zeros(nt, int), 1 + np.arange(nt), 2 + np.arange(nt)], 1)
+    elif kind == 7:    # several 1024-column chunks per row: the per-unit list / common-ancestor / zone logic of K4
+        from fluxpy_b200 import meshes
+        n = int(rng.integers(24, 44))
+        V, F = meshes.gaussian_crater(n, int(rng.integers(0, 1000)), dtype=np.float64)
+        V[:, 2] *= float(rng.choice([0.3, 1.0, 2.5]))     # flatter / steeper relief: more or fewer occluded rays
     else:              # translated far from the origin (float32 resolution of the coordinates matters)
         from fluxpy_b200 import meshes
         n = int(rng.integers(3, 14))
@@ -122,8 +127,8 @@ def main():
         N = random_normals(rng, V, F)
         nf = len(F)
         I = J = None
-        if rng.random() < 0.5:
-            I = rng.integers(0, nf, int(rng.integers(0, nf + 3))).astype(np.int64)
+        if rng.random() < 0.5 or nf > 1000:
+            I = rng.integers(0, nf, int(rng.integers(0, min(nf, 160) + 3))).astype(np.int64)
         if rng.random() < 0.5:
             J = rng.integers(0, nf, int(rng.integers(0, 2*nf + 3))).astype(np.int64)
         eps = float(rng.choice([1e-5, 1e-5, 1e-7, 0.0, -1.0, 1e-2]))
@@ -139,6 +144,14 @@ def main():
             skipped += 1
             seed += 1
             continue
+        opts = {}
+        if rng.random() < 0.5:   # tunables must never change a result
+            for name, choices in (('sub_rows', [1, 3, 7, 32, 512]), ('host_expand', [0, 1]), ('fill_rows', [-1, 0, 1, 2, 8]),
+                                  ('shaft_filter', [0, 1]), ('top_nodes', [0, 0, 8, 64]), ('slab_limit', [0, 4, 1 << 30]),
+                                  ('blocks_per_sm', [1, 4]), ('host_threads', [0, 1, 3])):
+                if rng.random() < 0.4:
+                    opts[name] = int(rng.choice(choices))
+                    sm.set_option(name, opts[name])
         FO = oracle.get_form_factor_matrix(om, I, J, eps)
         FO.sort_indices()
         for hor in (0, 1):
@@ -152,7 +165,7 @@ def main():
                   and np.array_equal(FF.data.view(np.uint8), FO.data.view(np.uint8)))
             if not ok:
                 print(f'MISMATCH seed {seed} kind {kind} dtype {np.dtype(dtype).name} faces {nf} horizon {hor} zone {zone} '
-                      f'eps {eps} nnz {FF.nnz} vs oracle {FO.nnz}', flush=True)
+                      f'eps {eps} options {opts} nnz {FF.nnz} vs oracle {FO.nnz}', flush=True)
                 sys.exit(1)
         if rng.random() < 0.3 and nf <= 120:
             # query hooks on the same tree: visibility (BVH == brute force on the device == oracle), sun occlusion

@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 // sibling subtree that holds the target (X) is not tested: its inside is
                 // covered by phase B.
                 int xref = ~tleaf;
+                bool xbig = false; // kHor: the record that holds my target is larger than any zone
                 const bool fullpath = __any_sync(0xffffffffu, active && overshoot);
                 int nuse = fullpath ? nall : nsel;
                 if constexpr (kHor) {
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                         const int ref = __float_as_int(a.w);
                         if (tleaf >= rg.x && tleaf <= rg.y) {
                             xref = ref;
+                            if constexpr (kHor) xbig = rg.y - rg.x + 1 > A.zone_leaves;
                         } else if (child_hit(ray, rb, a, b, cc, tmax_a)) {
                             if (ref < 0) push_leaf(~ref);
                             else push_node(ref);
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     // target end: the ray arrives above the horizon of zone(j) and the tested interval does
                     // not run on past p_j as far as the zone's nearest other triangle -> nothing in zone(j)
                     // except j can be met: the walk starts at the zone's node
-                    if (active && tskip_unit) {
+                    if (active && (tskip_unit || xbig)) { // the walk ends (at C, or at my X) above every zone
                         const float4 h = __ldg(A.colH + scol);
                         const Real4<T> Nj = load_real4<T>(A.colN + scol);
                         const float st = -((float)Nj.x * ray.dx + (float)Nj.y * ray.dy + (float)Nj.z * ray.dz);

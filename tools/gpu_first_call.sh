@@ -31,6 +31,9 @@ echo "== launch list (durations) of one 4096-row slab, horizon on: K4, horizon_k
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${T}_launches_horizon.csv \
     python tools/prof_one.py 4096 317 horizon_skip=1 > $OUT/${T}_prof_one.log 2>&1
 grep -E "horizon_kernel|zone_kernel|col_horizon|trace_kernel" $OUT/${T}_launches_horizon.csv | awk -F'","' '{print $5, $NF}' | head -12
+echo "== compute-sanitizer on the horizon variant (small case, zone 32 so that the skip is taken)"
+compute-sanitizer --tool memcheck  python tools/sanitize_case.py horizon_zone=32 horizon_skip=1 2>&1 | tail -3 | tee $OUT/${T}_sanitizer_memcheck_horizon.log
+compute-sanitizer --tool racecheck python tools/sanitize_case.py horizon_zone=32 horizon_skip=1 2>&1 | tail -3 | tee $OUT/${T}_sanitizer_racecheck_horizon.log
 echo "== full capture of the horizon variant of K4 (second repetition)"
 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 -o $OUT/${T}_trace_horizon \
     python tools/prof_one.py 4096 317 horizon_skip=1 > /dev/null 2>&1

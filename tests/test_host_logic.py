@@ -293,3 +293,24 @@ def test_sharded_npz_roundtrip(tmp_path):
     scipy.sparse.save_npz(str(tmp_path / 'ref.npz'), FF)
     ref = scipy.sparse.load_npz(str(tmp_path / 'ref.npz'))
     assert np.array_equal(ref.data, back.data)
+
+
+def test_reference_own_unit_tests_on_the_cuda_backend():
+    """The reference's UNMODIFIED tests/test_shape.py, test_form_factors.py and
+    test_compressed_form_factors.py, run from /root/reference against CudaTrimeshShapeModel as the only
+    entry of flux.shape.trimesh_shape_models -- once through the reference's own row loop
+    (form_factors.py:11-72 calling get_visibility_1_to_N per row) and once through the fused assembly
+    installed by fluxpy_b200.integration -- plus the row loop vs fused cross-check on an occluded crater
+    (tools/run_reference_tests.py; kernels on the SIMT emulator here).  Build container only."""
+    if not os.path.isdir('/root/reference/src'):
+        pytest.skip('reference tree not present')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'run_reference_tests.py'), 'both'],
+                         capture_output=True, text=True, timeout=900)
+    text = out.stdout + out.stderr
+    assert out.returncode == 0, text[-4000:]
+    assert 'FAILED on the backend' not in text
+    for mode in ('loop', 'fused'):
+        assert f'[{mode}] reference tests run 7' in text
+        assert text.count(f'[{mode}] is_occluded adjudication') == 2
+    assert text.count('backend != exact convex answer on 0 faces') == 4
+    assert text.count('pattern identical: True') == 4

@@ -77,3 +77,67 @@ def check_against_reference_csr(FF, ref_indptr, ref_indices, ref_data, P, N, A, 
     ok = np.abs(ref_val[common] - t) <= (band/np.maximum(num[common], 1e-300) + 16*unit(dtype))*np.abs(t)
     assert ok.all(), 'reference value outside its own round-off bound: checker is wrong'
     return int(diff.sum())
+
+
+def heightfield_clearance(V, n, pi, PJ, ray_offset=1e-3):
+    """Independent geometric ground truth for centroid-to-centroid visibility on a regular-grid height field
+    triangulated as ``fluxpy_b200.meshes.grid_faces`` (cells split along the a-d diagonal) -- no ray/triangle
+    test, no BVH, no oracle code.  The surface is piecewise linear, so along the segment p_i -> p_j the
+    clearance g(s) = z_segment(s) - z_surface(x(s), y(s)) is piecewise linear with breakpoints where the
+    segment's xy-projection crosses a grid line x = x_k, y = y_k or a cell diagonal; the segment crosses the
+    surface (some triangle is hit before the target, from either side: shape.py:349-398 has no back-face
+    culling) iff g changes sign over the breakpoints.  Returns (gmin, gmax) over the breakpoints of every
+    target (+inf / -inf when there is none): visible iff gmin > 0 or gmax < 0; min(|gmin|, |gmax|) small =
+    a grazing pair that floating-point ray tracers may legitimately call either way."""
+    V = np.asarray(V, np.float64)
+    Z = V[:, 2].reshape(n, n)                   # Z[iy, ix]
+    x0, y0 = V[0, 0], V[0, 1]
+    h = (V[n*n - 1, 0] - x0)/(n - 1)
+    pi = np.asarray(pi, np.float64)
+    PJ = np.asarray(PJ, np.float64)
+    uA, vA, zA = (pi[0] - x0)/h, (pi[1] - y0)/h, pi[2]
+    uB, vB, zB = (PJ[:, 0] - x0)/h, (PJ[:, 1] - y0)/h, PJ[:, 2]
+    L = np.sqrt(((PJ - pi)**2).sum(1))
+    gmin = np.full(len(PJ), np.inf)
+    gmax = np.full(len(PJ), -np.inf)
+
+    def lerp_cell(iy0, ix0, iy1, ix1, f):
+        return Z[iy0, ix0]*(1 - f) + Z[iy1, ix1]*f
+
+    def account(s, height, ok):
+        nonlocal gmin, gmax
+        ok = ok & (s > 0) & (s < 1) & (s*L[:, None] > ray_offset)
+        g = zA + (zB - zA)[:, None]*s - height
+        gmin = np.minimum(gmin, np.where(ok, g, np.inf).min(1))
+        gmax = np.maximum(gmax, np.where(ok, g, -np.inf).max(1))
+
+    with np.errstate(divide='ignore', invalid='ignore'):
+        k = np.arange(n, dtype=np.float64)[None, :]
+        # grid lines u = k: the surface along the line is linear between the nodes (k, floor v), (k, floor v + 1)
+        s = (k - uA)/(uB - uA)[:, None]
+        ok = np.isfinite(s)
+        s = np.where(ok, s, 0.5)
+        v = vA + (vB - vA)[:, None]*s
+        c = np.clip(np.floor(v), 0, n - 2).astype(int)
+        kk = np.broadcast_to(k.astype(int), c.shape)
+        account(s, lerp_cell(c, kk, c + 1, kk, v - c), ok)
+        # grid lines v = k
+        s = (k - vA)/(vB - vA)[:, None]
+        ok = np.isfinite(s)
+        s = np.where(ok, s, 0.5)
+        u = uA + (uB - uA)[:, None]*s
+        c = np.clip(np.floor(u), 0, n - 2).astype(int)
+        account(s, lerp_cell(kk, c, kk, c + 1, u - c), ok)
+        # cell diagonals u - v = k: between the nodes (floor u, floor v) and (floor u + 1, floor v + 1)
+        k = np.arange(-(n - 1), n, dtype=np.float64)[None, :]
+        wA, wB = uA - vA, uB - vB
+        s = (k - wA)/(wB - wA)[:, None]
+        ok = np.isfinite(s)
+        s = np.where(ok, s, 0.5)
+        u = uA + (uB - uA)[:, None]*s
+        v = u - k                                # exactly on the diagonal
+        cu = np.clip(np.floor(u), 0, n - 2).astype(int)
+        cv = np.clip(cu - k.astype(int), 0, n - 2)
+        ok = ok & (cu - k.astype(int) >= 0) & (cu - k.astype(int) <= n - 2)
+        account(s, lerp_cell(cv, cu, cv + 1, cu + 1, u - cu), ok)
+    return gmin, gmax

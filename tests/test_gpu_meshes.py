@@ -105,6 +105,43 @@ def test_float64_planetocentric_coordinates(mods):
     assert (sm._get_visibility(I, np.arange(nf)) == sm._get_visibility(I, np.arange(nf), _bruteforce=True)).all()
 
 
+@pytest.mark.parametrize('case', [(72, np.float32, 1.0), (159, np.float32, 1.0), (72, np.float64, 1.0)])
+def test_visibility_and_csr_pattern_equal_heightfield_geometry(mods, case):
+    """The CUDA path against a ground truth that is neither the oracle nor a ray tracer: the clearance of
+    the centroid-to-centroid segment over the piecewise-linear height field at every grid-line / diagonal
+    crossing (tests/helpers.py::heightfield_clearance).  BASELINE.json's criterion for the visibility mask --
+    at least 99.99 % agreement, every disagreement a grazing ray within 1e-6 -- on sampled rows x all
+    columns of the 10k- and 50k-face craters: no disagreement at all outside the 1e-6 band, and the CSR rows
+    hold exactly the cull survivors that the geometry calls visible.  (Unit scale only: in km units the
+    reference's absolute 1e-3 ray offset no longer clears the float32 rounding of the centroid for rays within
+    ~1e-2 rad of the source plane, which then hit their own triangle -- DESIGN.md section 5.)"""
+    from tests import helpers
+    n, dtype, scale = case
+    V, F = mods['meshes'].gaussian_crater(n, 0, dtype=dtype, scale=scale)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    nf = sm.num_faces
+    rows = np.linspace(0, nf - 1, 48 if n < 100 else 12).astype(np.int64)   # (the NumPy check is the slow part)
+    vis = sm.get_visibility(rows, np.arange(nf))
+    FF = mods['ff'].get_form_factor_matrix(sm, rows)
+    stored = FF.toarray() != 0
+    P = sm.P.astype(np.float64)
+    checked = grazing = 0
+    for r, i in enumerate(rows):
+        gmin, gmax = helpers.heightfield_clearance(V, n, P[i], P, ray_offset=1e-3)
+        geo = (gmin > 0) | (gmax < 0)
+        clear = np.minimum(np.abs(gmin), np.abs(gmax)) > 1e-6*scale
+        clear[i] = False
+        assert ((vis[r] == geo) | ~clear).all()
+        # a stored entry is a visible pair; a visible pair facing both ways is stored (cull: form_factors.py:46-52)
+        assert not (stored[r] & ~geo & clear).any()
+        d = P - P[i]
+        num = np.maximum(0, d@sm.N[i].astype(np.float64))*np.maximum(0, -(d*sm.N.astype(np.float64)).sum(1))
+        assert stored[r][geo & clear & (num > 1e-4*scale*scale)].all()
+        checked += int(clear.sum())
+        grazing += int((~clear).sum()) - 1
+    assert checked > 0.99*(len(rows)*(nf - 1)) and grazing < 1e-2*checked
+
+
 def test_ingersoll_bowl(mods):
     """Config 1 stand-in: exactly flat plane faces cull to nothing, faces inside
     the spherical cap see each other (concave), block == slice."""

@@ -141,3 +141,25 @@ def heightfield_clearance(V, n, pi, PJ, ray_offset=1e-3):
         ok = ok & (cu - k.astype(int) >= 0) & (cu - k.astype(int) <= n - 2)
         account(s, lerp_cell(cv, cu, cv + 1, cu + 1, u - cu), ok)
     return gmin, gmax
+
+
+def heightfield_sun_clearance(V, n, P, N, D, eps=None):
+    """Same geometry for the sun-occlusion query (shape.py:400-421): the ray from P[i] + 1e-3*N[i] along D,
+    followed to where it leaves the mesh's xy bounding box; blocked iff its clearance over the surface is
+    negative at some grid-line / diagonal crossing.  Returns gmin per face (+inf: no crossing inside)."""
+    V = np.asarray(V, np.float64)
+    P = np.asarray(P, np.float64)
+    N = np.asarray(N, np.float64)
+    D = np.asarray(D, np.float64)
+    if eps is None:
+        eps = 1e3*np.finfo(np.float32).resolution
+    lo, hi = V[:, :2].min(0), V[:, :2].max(0)
+    out = np.empty(len(P))
+    for i in range(len(P)):
+        org = P[i] + eps*N[i]
+        with np.errstate(divide='ignore'):
+            t_exit = np.where(D[:2] > 0, (hi - org[:2])/D[:2], np.where(D[:2] < 0, (lo - org[:2])/D[:2], np.inf)).min()
+        end = org + (t_exit + 1e-6)*D            # a hair past the boundary, so that the crossing of the mesh's last grid line counts
+        gmin, _ = heightfield_clearance(V, n, org, end[None, :], ray_offset=0.0)
+        out[i] = gmin[0]
+    return out

@@ -142,6 +142,30 @@ def test_visibility_and_csr_pattern_equal_heightfield_geometry(mods, case):
     assert checked > 0.99*(len(rows)*(nf - 1)) and grazing < 1e-2*checked
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_sun_occlusion_equals_heightfield_geometry(mods, dtype):
+    """Next row N1 on the CUDA path against the geometric ground truth (tests/helpers.py::
+    heightfield_sun_clearance): low sun over the 10k-face crater, one direction for all faces and per-face
+    directions (shape.py:400-421 accepts both); get_direct_irradiance follows (shape.py:190-244)."""
+    from tests import helpers
+    n = 72
+    V, F = mods['meshes'].gaussian_crater(n, 0, dtype=dtype)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    faces = np.arange(sm.num_faces)
+    for elev, az in ((3.0, 0.3), (12.0, 2.1)):
+        e = np.deg2rad(elev)
+        D = np.array([np.cos(e)*np.cos(az), np.cos(e)*np.sin(az), np.sin(e)]).astype(dtype)
+        gmin = helpers.heightfield_sun_clearance(V, n, sm.P, sm.N, D)
+        clear = np.abs(gmin) > 1e-6
+        occ = sm.is_occluded(faces, D)
+        assert (occ == (gmin < 0))[clear].all() and clear.mean() > 0.995
+        assert (sm.is_occluded(faces, np.tile(D, (sm.num_faces, 1))) == occ).all()
+        E = sm.get_direct_irradiance(1365.0, D)
+        lit = clear & (gmin > 0)
+        assert np.allclose(E[lit], 1365.0*np.maximum(0, sm.N[lit]@D), rtol=1e-6) and (E[clear & (gmin < 0)] == 0).all()
+        assert 0.02 < occ.mean() < 0.98
+
+
 def test_ingersoll_bowl(mods):
     """Config 1 stand-in: exactly flat plane faces cull to nothing, faces inside
     the spherical cap see each other (concave), block == slice."""

@@ -188,6 +188,56 @@ def test_ingersoll_bowl(mods):
     assert abs(FF[i, j]/sm.A[j] - 1/(4*np.pi*R*R)) < 0.05/(4*np.pi*R*R)
 
 
+def test_ingersoll_analytic_flux_and_temperature(mods):
+    """Config 1 end to end against the ANALYTIC solution of the spherical-cap crater (Ingersoll et al.; reference
+    src/flux/ingersoll.py:19-33 for T in shadow, examples/spherical_crater/collect_data.py:180-238 for the
+    absorbed flux Q on the plane / in shadow / in the sun): beta = 40 deg, rc = 0.8, sun at 15 deg, F0 = 1000,
+    rho = 0.3, emiss = 0.99 (collect_data.py:8-30).  Form factors and sun occlusion from the CUDA path, the two
+    Jacobi solves of model.py:8-24 written out with SciPy products (and, on a real device, by the device-resident
+    solver as well).  The error is the mesh's: it shrinks as the grid is refined."""
+    beta, rc, e0, F0, rho, emiss = np.deg2rad(40), 0.8, np.deg2rad(15), 1000.0, 0.3, 0.99
+    sigma = 5.670374419e-8
+    f = (1 - np.cos(beta))/2
+    b = f*(emiss + rho*(1 - f))/(1 - rho*f)
+    T_gt = (F0*np.sin(e0)*f*(1 - rho)/(1 - rho*f)*(1 + rho*(1 - f)/emiss)/sigma)**0.25
+    D = np.array([np.cos(e0), 0, np.sin(e0)])
+
+    def jacobi(FF, E, r):                        # solve.py:36-45, albedo on the right
+        B = E.copy()
+        for _ in range(1000):
+            B1 = E + FF@(r*B)
+            if abs(B1 - B).max() <= 1e-13*abs(E).max():
+                return B1
+            B = B1
+        raise AssertionError('no convergence')
+
+    med = {}
+    for n in (41, 61):
+        V, F = mods['meshes'].ingersoll_bowl(n, dtype=np.float64)
+        sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+        FF = mods['ff'].get_form_factor_matrix(sm)
+        E = sm.get_direct_irradiance(F0, D)
+        B = jacobi(FF, E, rho)
+        Q = emiss*jacobi(FF, FF@((1 - rho)*B), 1.0) + (1 - rho)*B
+        Rc, h = np.sqrt((sm.P[:, :2]**2).sum(1)), 2/(n - 1)
+        plane, crater = Rc > rc + 2*h, Rc < rc - 2*h          # leave out the cells the rim passes through
+        shadow, sun = crater & (E == 0), crater & (E > 0)
+        elev = np.maximum(0, np.pi/2 - np.arccos(np.clip(sm.N@D, -1, 1)))
+        assert plane.sum() > 0.2*len(F) and shadow.sum() > 0.1*len(F) and sun.sum() > 0.1*len(F)
+        assert np.allclose(Q[plane], (1 - rho)*F0*np.sin(e0), rtol=1e-12)
+        rs = abs(Q[shadow]/((1 - rho)*F0*b*np.sin(e0)) - 1)
+        ru = abs(Q[sun]/((1 - rho)*F0*(np.sin(elev[sun]) + b*np.sin(e0))) - 1)
+        T = (Q/(emiss*sigma))**0.25
+        med[n] = (np.median(rs), np.median(ru), abs(np.median(T[shadow])/T_gt - 1))
+        assert med[n][0] < 0.03 and rs.max() < 0.10 and med[n][1] < 0.01 and ru.max() < 0.02 and med[n][2] < 0.01
+        import torch
+        if torch.cuda.is_available():            # the device-resident solver on the same matrix
+            from fluxpy_b200 import solve, get_form_factor_matrix_device
+            Td = solve.compute_steady_state_temp(get_form_factor_matrix_device(sm), E, rho, emiss)
+            assert np.allclose(Td, T, rtol=1e-9)
+    assert all(med[61][k] < med[41][k] for k in range(3))
+
+
 def test_coincident_faces_tie_rule(mods):
     """Two copies of the same triangle have the same hit distance: the oracle's
     index-ordered closest hit keeps the later one.  The CUDA any-hit form must

@@ -24,7 +24,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 #   FLUXB200_TEST_EMU=1 python -m pytest tests -m gpu      (conftest skips what needs a real device or is too large)
 SUBSET = ('test_sphere_fixtures or test_sphere_shape_api or (test_crater_vs_oracle_and_golden and not case2) '
           'or test_steady_state_temperature or test_edge_cases or test_fill_kernel_variants_agree '
-          'or test_coincident_faces_tie_rule or test_ingersoll_bowl or test_random_triangle_soup')
+          'or test_coincident_faces_tie_rule or test_ingersoll_bowl or test_random_triangle_soup '
+          # independent ground truths: exact convex clipping, height-field clearance, analytic Ingersoll crater
+          'or test_is_occluded_equals_exact_convex_answer '
+          'or (test_visibility_and_csr_pattern_equal_heightfield_geometry and case0) '
+          'or test_ingersoll_analytic_flux_and_temperature')
 
 
 @pytest.fixture(scope='module')

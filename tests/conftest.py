@@ -38,7 +38,7 @@ def pytest_configure(config):
 
 # gpu-tier tests that hand torch CUDA tensors (device pointers) to the library or need NCCL: no emulator run
 NEEDS_REAL_DEVICE = ('test_device_resident_radiosity_and_steady_state', 'test_block_extraction_and_lowrank_feed',
-                     'test_two_rank_sharded_assembly_and_solve')
+                     'test_two_rank_sharded_assembly_and_solve', 'test_ingersoll_device_resident_solver')
 # too large for the emulator's ~2 M rays/s (full 50k / 82k / 200k-face matrices)
 TOO_LARGE_FOR_EMU = ('test_closed_cratered_body_82k_sampled_rows', 'test_full_50k_matrix_properties',
                      'test_slab_properties_at_full_size', 'test_culling_structures_are_conservative_at_scale')

@@ -15,6 +15,7 @@ Without a CUDA device the library's CUDA sources run on the SIMT emulator (tools
 infrastructure).  Nothing here is read on the GPU box: /root/reference does not exist there.
 
     python tools/run_reference_tests.py [loop|fused|both] [unittest name filters ...]
+    FLUXB200_TEST_HORIZON=64 python tools/run_reference_tests.py     # the same with the horizon skip of K4 on
 
 Shims, none of which touches the path under test: ``cached_property`` (package absent; functools has the
 same decorator), ``np.product`` (removed in NumPy 2; compressed_form_factors.py:313 still calls it), a
@@ -85,6 +86,15 @@ def prepare(mode):
     import flux.shape
     import flux.form_factors
     from fluxpy_b200 import CudaTrimeshShapeModel, integration
+    zone = os.environ.get('FLUXB200_TEST_HORIZON')
+    if zone:  # as tests/conftest.py: every shape model with the trace kernel's horizon skip on (value = zone size)
+        plain_init = CudaTrimeshShapeModel.__init__
+
+        def init_with_horizon(self, *args, **kwargs):
+            plain_init(self, *args, **kwargs)
+            self.set_option('horizon_zone', int(zone))
+            self.set_option('horizon_skip', 1)
+        CudaTrimeshShapeModel.__init__ = init_with_horizon
     reference_loop = flux.form_factors.get_form_factor_matrix
     if mode == 'fused':
         integration.install()

@@ -44,9 +44,10 @@ struct fluxb200_mesh {
     int slab_limit_opt = 1 << 30;
     int blocks_per_sm = 4;
     int shaft_filter_opt = 1;
-    // horizon skip of the trace kernel (horizon.cuh).  Off by default: validated bit for bit against the
-    // oracle on the SIMT emulator (tools/simt) but not yet measured on a B200.
-    int horizon_skip_opt = 0;
+    // horizon skip of the trace kernel (horizon.cuh).  On by default since round 2: bit-identical CSRs over the
+    // whole gpu tier on a B200 with the skip on and off, trace kernel 49.2 -> 34.5 ms per 4096-row slab of the
+    // 200k-face crater (profiles/r02a_*); the horizons cost 6.0 ms once per mesh / change of P, N.
+    int horizon_skip_opt = 1;
     int horizon_zone_opt = 1023; // Z: leaves per near zone (below the 1024-column chunk: the upward walk must end above every zone)
     bool hz_dirty = true;       // P, N or the tree changed since the horizons were computed
     DevBuf hz, zone_node, zone_up, colH;

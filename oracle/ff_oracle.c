@@ -332,6 +332,22 @@ static inline void closest_hit(const oracle_scene *s, int use_bvh, const float o
     else closest_hit_brute(s, org, dir, tnear, tfar, prim);
 }
 
+/* Threads an OpenMP region with this request really gets (bench.py prints it next to
+ * `cores`: under torchrun OMP_NUM_THREADS=1 is exported and a default-sized team is one thread). */
+int oracle_team_size(int nthreads) {
+    int got = 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+#endif
+    (void)nthreads;
+    return got;
+}
+
 /* rtcIntersect1M stand-in: stream of n single rays (shape.py:375-390).  On a
  * hit tfar <- t, prim_id <- triangle, geom_id <- 0; otherwise untouched. */
 void oracle_intersect1M(const oracle_scene *s, size_t n, const float *org, const float *dir,

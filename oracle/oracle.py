@@ -60,6 +60,8 @@ def lib():
         f.restype = vp
         f.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz, ctypes.c_double, i32, i32]
         getattr(L, 'oracle_face_geometry_' + sfx).argtypes = [vp, vp, sz, vp, vp, vp]
+    L.oracle_team_size.argtypes = [i32]
+    L.oracle_team_size.restype = i32
     L.oracle_ff_nnz.restype = ctypes.c_int64
     L.oracle_ff_nnz.argtypes = [vp]
     L.oracle_ff_tested.restype = ctypes.c_int64
@@ -93,6 +95,11 @@ def face_geometry(V, F):
     getattr(lib(), 'oracle_face_geometry_' + _sfx(V.dtype))(
         _ptr(V), _ptr(F64), nf, _ptr(P), _ptr(N), _ptr(A))
     return P, N, A
+
+
+def team_size(nthreads=0):
+    """OpenMP threads a region asked for ``nthreads`` (0 = default) really gets."""
+    return int(lib().oracle_team_size(int(nthreads)))
 
 
 class OracleScene:

@@ -31,8 +31,9 @@ def pytest_configure(config):
 
         def init_with_horizon(self, *args, **kwargs):
             plain_init(self, *args, **kwargs)
-            self.set_option('horizon_zone', int(zone))
-            self.set_option('horizon_skip', 1)
+            if int(zone) > 0:
+                self.set_option('horizon_zone', int(zone))
+            self.set_option('horizon_skip', 1 if int(zone) > 0 else 0)   # 0: the skip (default on) switched off
         shape.CudaTrimeshShapeModel.__init__ = init_with_horizon
 
 

@@ -239,6 +239,46 @@ void k4_horizons(const Model *M, int zone_leaves, float *hor) {
     }
 }
 
+/* Variant "multi-level source horizon": further, larger source-side zones (leaf counts g_src_zone[k] with
+ * horizons g_src_hor[k], valid for the sampled rows only); a batch skips the records inside the largest zone
+ * whose horizon all its rays clear. */
+double g_chist[20];
+double *k4_chist(void) { return g_chist; }
+static int g_src_levels = 0;
+static int g_src_zone[4];
+static const float *g_src_hor[4];
+void k4_set_source_levels(int nlev, const int *zones, const float **hors) {
+    g_src_levels = nlev;
+    for (int k = 0; k < nlev && k < 4; ++k) { g_src_zone[k] = zones[k]; g_src_hor[k] = hors[k]; }
+}
+/* horizons of the given faces only (vertices + edge midpoints + centroid sampled; model accuracy) */
+void k4_horizons_rows(const Model *M, int zone_leaves, int nrows, const int *rows, float *hor) {
+    const int n = M->n;
+    for (int r = 0; r < nrows; ++r) {
+        const int f = rows[r];
+        const int z = zone_of(M, n - 1 + M->face_leaf[f], zone_leaves);
+        int lo, hi;
+        if (z >= n - 1) { lo = hi = z - (n - 1); } else { lo = M->first[z]; hi = M->last[z]; }
+        const double *P = M->P + 3 * f, *N = M->N + 3 * f;
+        double best = -1.0;
+        for (int k = lo; k <= hi; ++k) {
+            const int g = M->leaf_face[k];
+            if (g == f) continue;
+            const float *v[3] = {M->V + 3 * M->F[3 * g], M->V + 3 * M->F[3 * g + 1], M->V + 3 * M->F[3 * g + 2]};
+            for (int a = 0; a <= 2; ++a)
+                for (int b = 0; a + b <= 2; ++b) {
+                    const double wa = a / 2.0, wb = b / 2.0, wc = 1.0 - wa - wb;
+                    double d[3], l2 = 0, h = 0;
+                    for (int c = 0; c < 3; ++c) { d[c] = wa * v[0][c] + wb * v[1][c] + wc * v[2][c] - P[c]; l2 += d[c] * d[c]; h += d[c] * N[c]; }
+                    const double l = sqrt(l2);
+                    if (l < 1e-6 * M->scale) { best = INFINITY; continue; }
+                    if (h / l > best) best = h / l;
+                }
+        }
+        hor[f] = (float)best;
+    }
+}
+
 static int zone64(const Model *M, int leafnode) { /* largest ancestor (or the leaf) holding at most 64 leaves */
     int x = leafnode;
     while (M->parent[x] >= 0) {
@@ -415,6 +455,17 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                         out[23] += tgt_skip[l];
                     }
                     out[24] += src_skip;
+                    for (int k = 0; k < g_src_levels; ++k) { /* larger source zones, smallest first */
+                        int ok = src_skip;
+                        for (int l = 0; l < nb && ok; ++l) {
+                            const double es = Ni[0] * ray[l].dx + Ni[1] * ray[l].dy + Ni[2] * ray[l].dz;
+                            if (!(es > g_src_hor[k][i] + g_margin)) ok = 0;
+                        }
+                        if (!ok) break;
+                        const int sz2 = zone_of(M, n - 1 + ileaf, g_src_zone[k]);
+                        node_range(M, sz2, &szlo, &szhi);
+                        out[25 + k] += 1;
+                    }
                 }
                 /* phase A */
                 int sp[32] = {0}, cand[32] = {0}, xref[32];
@@ -479,6 +530,7 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                 out[3] += b_max;
                 /* phase C */
                 int c_max = 0, f_max = 0;
+                int useen[4096], nseen = 0; /* distinct nodes any ray of the batch visits (a packet traversal's count) */
                 for (int l = 0; l < nb; ++l) {
                     int it = 0;
                     while (sp[l] > 0) {
@@ -488,6 +540,9 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                         const int tz = zone64(M, n - 1 + tleaf[l]);
                         for (;;) {
                             ++it; out[16 + side] += 1;
+                            { int k = 0; while (k < nseen && useen[k] != node) ++k;
+                              if (k == nseen && nseen < 4096) { useen[nseen++] = node; } }
+                            { int sz = M->last[node] - M->first[node] + 1, lg = 0; while ((1 << (lg + 1)) <= sz) ++lg; g_chist[lg < 20 ? lg : 19] += 1; }
                             const int lc = M->left[node], rc = M->right[node];
                             const int h0 = node_hit(M, lc, &ray[l]), h1 = node_hit(M, rc, &ray[l]);
                             if (h0 && lc >= n - 1 && lc - (n - 1) != tleaf[l]) { cand[l]++; if (in_zone(M, szone, lc - (n - 1))) out[19] += 1; if (in_zone(M, tz, lc - (n - 1))) out[20] += 1; }
@@ -501,7 +556,7 @@ void k4_count(const Model *M, int nrows, const int *rows, int chunk, double eps,
                     if (it > c_max) c_max = it;
                     if (cand[l] > f_max) f_max = cand[l];
                 }
-                out[4] += c_max; out[9] += f_max;
+                out[4] += c_max; out[9] += f_max; out[29] += nseen;
             }
         }
     }

@@ -15,7 +15,7 @@ SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 OVERFLOW = 2
 
 #: every symbol include/fluxb200.h declares

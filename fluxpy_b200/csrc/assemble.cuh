@@ -78,6 +78,11 @@ template <class T> struct TraceArgs {
     const float4 *colH;             // per sorted column: (hor, rmin, zone node, up code of the zone node)
     int zone_leaves;                // Z
     float pert;                     // ray perturbation + Pluecker slack, in length units
+    // second-generation kernel (trace2.cuh)
+    const float4 *chunk_info;       // 3 float4 per chunk of 1024 sorted columns (chunk_info_kernel)
+    int2 *lost;                     // (row of this launch, sorted column) of rays to be resolved by resolve_lost_kernel
+    unsigned *lost_count;           // entries appended to `lost`
+    unsigned lost_cap;
 };
 
 // explicit shared-space loads / stores from a 32-bit shared address kept in a register: the
@@ -720,18 +725,37 @@ template <class T> struct FillArgs {
 };
 
 // One CTA = 8 consecutive rows (one per warp) x one segment of the column groups (blockIdx.y; the
-// row's entry count before the segment comes from K6a's per-group counts).  Per group of 1024 columns the CTA
-// gathers P, N, A of the group's columns into shared memory once (the gather through `cols` and
-// the L2 reads are shared by the 8 rows), then every warp emits its row's entries of the group.
+// row's entry count before the segment comes from K6a's per-group counts).  A group of 1024 columns is
+// taken in two halves of 512: the CTA gathers P, N, A of the half's columns into shared memory once --
+// ALREADY CONVERTED TO DOUBLE (round 1 converted per stored entry: 13 F2F per entry kept the XU pipe 53 %
+// busy and the kernel at 20 % of the HBM write bandwidth) -- the gather through `cols` and the L2 reads
+// are shared by the 8 rows; then every warp emits its row's entries of the half, two entries per lane
+// and iteration (independent fp64 chains).
 constexpr int kFillGroup = 1024;
-template <class T> constexpr size_t emit_smem_bytes() { return 2 * sizeof(Real4<T>) * kFillGroup; }
+constexpr int kFillHalf = 512;
+struct __align__(16) EmitCol { double px, py, pz, area, nx, ny, nz, pad; }; // 64 B per staged column
+template <class T> constexpr size_t emit_smem_bytes() { return sizeof(EmitCol) * kFillHalf; }
+
+// F_ij = max(0, n_i.d) max(0, -n_j.d) A_j / (pi r^4), d = p_j - p_i, in fp64 from the model-dtype inputs
+// (form_factors.py:46-47 evaluated directly, :62-64); the operation order of numerator<T>() above
+__device__ __forceinline__ double form_factor_value(double pix, double piy, double piz, double nix, double niy,
+                                                    double niz, const EmitCol &c) {
+    const double dx = __dsub_rn(c.px, pix), dy = __dsub_rn(c.py, piy), dz = __dsub_rn(c.pz, piz);
+    double a = __fma_rn(nix, dx, __fma_rn(niy, dy, __dmul_rn(niz, dz)));
+    double b = -__fma_rn(c.nx, dx, __fma_rn(c.ny, dy, __dmul_rn(c.nz, dz)));
+    a = a > 0.0 ? a : 0.0;
+    b = b > 0.0 ? b : 0.0;
+    const double num = __dmul_rn(a, b); // (j == i: d == 0, so num == 0 and r2 == 0 -> 0, as row_data[i == J] = 0)
+    const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
+    const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                  // :62
+    return sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, c.area), sden);     // :63-64
+}
 
 template <class T>
 __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
-    Real4<T> *colP_s = reinterpret_cast<Real4<T> *>(stage_raw), *colN_s = colP_s + kFillGroup;
-    __shared__ int colj_s[kFillGroup];
-    __shared__ uint16_t list_s[kFillWarps][kFillGroup];
+    EmitCol *col_s = reinterpret_cast<EmitCol *>(stage_raw);
+    __shared__ uint16_t list_s[kFillWarps][kFillHalf];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * kFillWarps + warp;
     // blockIdx.y = segment of the column groups (enough CTAs for a small row slab)
@@ -751,29 +775,33 @@ __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A)
     }
     const int i = live ? A.rows[r] : 0;
     const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
-    for (int g = g_begin; g < g_end; ++g) {
-        __syncthreads(); // the previous group's columns are no longer read
-        for (int c = threadIdx.x; c < kFillGroup; c += kFillThreads) {
-            const int q = g * kFillGroup + c;
+    const double pix = (double)Pi.x, piy = (double)Pi.y, piz = (double)Pi.z;
+    const double nix = (double)Ni.x, niy = (double)Ni.y, niz = (double)Ni.z;
+    for (int gh = 2 * g_begin; gh < 2 * g_end; ++gh) {
+        const int q0 = gh * kFillHalf; // first column of this half
+        if (q0 >= A.n) break;          // (uniform: the second half of the last group may be empty)
+        __syncthreads(); // the previous half's columns are no longer read
+        for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
+            const int q = q0 + c;
             if (q < A.n) {
                 const int j = A.cols[q];
-                colj_s[c] = j;
-                colP_s[c] = load_real4<T>(A.faceP + j);
-                colN_s[c] = load_real4<T>(A.faceN + j);
+                const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
+                col_s[c] = EmitCol{(double)Pj.x, (double)Pj.y, (double)Pj.z, (double)Pj.w,
+                                   (double)Nj.x, (double)Nj.y, (double)Nj.z, 0.0};
             }
         }
         __syncthreads();
         if (!live) continue;
-        const int wi = g * 32 + lane;
-        uint32_t word = wi < A.nwords ? jb[wi] : 0u;
+        const int wi = gh * 16 + lane;
+        uint32_t word = (lane < 16 && wi < A.nwords) ? jb[wi] : 0u;
         const int c = __popc(word);
         int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < 16; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int total = __shfl_sync(0xffffffffu, incl, 15);
         if (total == 0) continue;
         int p = incl - c;
         while (word) { // ascending positions of my word's set bits
@@ -781,24 +809,25 @@ __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A)
             word &= word - 1;
         }
         __syncwarp();
-        for (int e = lane; e < total; e += 32) {
-            const int cpos = (int)list_s[warp][e];
-            const int j = colj_s[cpos];
-            const Real4<T> Pj = colP_s[cpos], Nj = colN_s[cpos];
-            double dx, dy, dz;
-            double num = numerator<T>(Pi, Ni, Pj, Nj, dx, dy, dz);
-            if (j == i) num = 0.0;
-            const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
-            const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                           // :62
-            const double v = sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, (double)Pj.w), sden); // :63-64
-            const int64_t dst = off + e;
+        for (int e = lane; e < total; e += 64) {
+            const int e1 = e + 32;
+            const bool two = e1 < total;
+            const int c0 = (int)list_s[warp][e], c1 = two ? (int)list_s[warp][e1] : c0;
+            const double v0 = form_factor_value(pix, piy, piz, nix, niy, niz, col_s[c0]);
+            const double v1 = form_factor_value(pix, piy, piz, nix, niy, niz, col_s[c1]);
             // streaming stores: the CSR is written once and must not push the mesh and BVH, which a
             // concurrently running trace kernel lives on, out of L2
-            __stcs(A.data + dst, (T)v);
-            const int q = g * kFillGroup + cpos;
+            const int64_t dst = off + e;
+            __stcs(A.data + dst, (T)v0);
+            if (two) __stcs(A.data + dst + 32, (T)v1);
             if (A.indices) {
-                if (A.index_width == 4) __stcs(reinterpret_cast<int *>(A.indices) + dst, q);
-                else __stcs(reinterpret_cast<long long *>(A.indices) + dst, (long long)q);
+                if (A.index_width == 4) {
+                    __stcs(reinterpret_cast<int *>(A.indices) + dst, q0 + c0);
+                    if (two) __stcs(reinterpret_cast<int *>(A.indices) + dst + 32, q0 + c1);
+                } else {
+                    __stcs(reinterpret_cast<long long *>(A.indices) + dst, (long long)(q0 + c0));
+                    if (two) __stcs(reinterpret_cast<long long *>(A.indices) + dst + 32, (long long)(q0 + c1));
+                }
             }
         }
         __syncwarp();
@@ -889,7 +918,10 @@ __global__ void col_gather_kernel(const uint32_t *__restrict__ pos, const int *_
     const int q = (int)pos[s];
     const int f = cols[q];
     colP[s] = faceP[f];
-    colN[s] = faceN[f];
+    Real4<T> Nf = faceN[f];
+    // .w: 8 * 2^-24 * max|N_k| -- the target's share of the float32 cull's error bound (trace2.cuh: cull_keep)
+    Nf.w = (T)(4.76837158e-7f * fmaxf(fmaxf(fabsf((float)Nf.x), fabsf((float)Nf.y)), fabsf((float)Nf.z)));
+    colN[s] = Nf;
     col_face[s] = f;
     col_leaf[s] = face_leaf[f];
     rank_of_pos[q] = s;

@@ -17,6 +17,7 @@
 #include "blockops.cuh"
 #include "horizon.cuh"
 #include "trace.cuh"
+#include "trace2.cuh"
 #include "host_expand.h"
 
 
@@ -51,6 +52,9 @@ struct fluxb200_mesh {
     int horizon_zone_opt = 1023; // Z: leaves per near zone (below the 1024-column chunk: the upward walk must end above every zone)
     bool hz_dirty = true;       // P, N or the tree changed since the horizons were computed
     DevBuf hz, zone_node, zone_up, colH;
+    // trace kernel generation: 2 = warp-shared traversal queue (trace2.cuh), 1 = per-lane stacks (assemble.cuh)
+    int trace_variant_opt = 2;
+    DevBuf chunk_info, lost; // lost: [0] count, then (row, column) pairs of rays for resolve_lost_kernel
     float ms_build = 0.f;
     float scene_h[7] = {};
 
@@ -373,6 +377,15 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
             M->rank_of_pos.as<int>());
         FB_CUDA(cudaGetLastError());
         launches += 2 + (M->sorter.launches - l0);
+        { // per-chunk data shared by every row (trace2.cuh)
+            const int nchunks = (int)ceil_div((int64_t)n, kChunkCols);
+            M->chunk_info.reserve(sizeof(float4) * 3 * (size_t)nchunks);
+            chunk_info_kernel<T><<<blocks_for((int64_t)nchunks * 32, B), B, 0, st>>>(
+                M->colP.as<Real4<T>>(), M->col_leaf.as<int>(), (int)n, nchunks, M->leaf_up.as<int>(),
+                M->node_up.as<int>(), M->node_range.as<int2>(), M->ninternal, M->chunk_info.as<float4>());
+            FB_CUDA(cudaGetLastError());
+            ++launches;
+        }
         if (M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0) {
             const int nf = (int)M->nf;
             if (M->hz_dirty) { // from the shape model's CURRENT P, N
@@ -398,7 +411,7 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
 // K4 for rows [row0, row0 + mr) of the uploaded index set
 template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, uint32_t *bits,
                                      uint32_t *row_counts, cudaStream_t st) {
-    TraceArgs<T> A;
+    TraceArgs<T> A{};
     A.faceP = M->faceP.as<Real4<T>>();
     A.faceN = M->faceN.as<Real4<T>>();
     A.rows = M->rows.as<int>() + row0;
@@ -431,6 +444,7 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.colH = hor ? M->colH.as<float4>() : nullptr;
     A.zone_leaves = M->horizon_zone_opt;
     A.pert = horizon_pert(M);
+    A.chunk_info = M->chunk_info.as<float4>();
     A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
@@ -442,7 +456,24 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     const int64_t units = (int64_t)mr * A.nchunks;
     const int grid = (int)std::min<int64_t>((int64_t)M->num_sms * M->blocks_per_sm,
                                             std::max<int64_t>(1, ceil_div(units, kTraceWarps)));
-    if (M->ntop > 0) trace_kernel<T, true><<<grid, kTraceThreads, smem, st>>>(A);
+    // second generation: needs the source path (depth + 1 records) and some of the target side in its list,
+    // and node ids in 26 bits; anything else takes the first-generation kernel
+    const bool gen2 = M->trace_variant_opt == 2 && M->ntop == 0 && M->max_depth + 1 + 8 <= kPathCap &&
+                      M->ninternal < (1 << kNodeBits);
+    if (gen2) {
+        // rays the kernel cannot finish in its bounded shared-memory stacks go to a list and are traced by
+        // resolve_lost_kernel right after it (typically 0.05 % of the rays: those grazing very many triangles)
+        const unsigned lost_cap = (unsigned)std::min<int64_t>(1 << 22, std::max<int64_t>(1024, (int64_t)mr * 256));
+        M->lost.reserve(16 + sizeof(int2) * (size_t)lost_cap);
+        A.lost_count = M->lost.as<unsigned>();
+        A.lost = reinterpret_cast<int2 *>(M->lost.as<unsigned char>() + 16);
+        A.lost_cap = lost_cap;
+        FB_CUDA(cudaMemsetAsync(A.lost_count, 0, sizeof(unsigned), st));
+        FB_CUDA(cudaFuncSetAttribute(trace2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)trace2_smem_bytes()));
+        trace2_kernel<T><<<grid, kTraceThreads, trace2_smem_bytes(), st>>>(A);
+        resolve_lost_kernel<T><<<M->num_sms * 4, 128, 0, st>>>(A);
+    } else if (M->ntop > 0) trace_kernel<T, true><<<grid, kTraceThreads, smem, st>>>(A);
     else if (hor) trace_kernel<T, false, true><<<grid, kTraceThreads, 0, st>>>(A);
     else trace_kernel<T, false><<<grid, kTraceThreads, 0, st>>>(A);
     FB_CUDA(cudaGetLastError());
@@ -562,8 +593,10 @@ template <class T> void ff_fill(fluxb200_mesh *M, int index_width, int destinati
     FB_REQUIRE(M->have_count, "fluxb200_ff_fill: no preceding fluxb200_ff_count on this handle");
     FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
     FB_REQUIRE(destination >= 0 && destination <= 2, "destination must be 0, 1 or 2");
+    // int32 must hold the column positions always, and the entry offsets only where indptr is emitted in the
+    // index dtype (host / caller buffers); the library's own device CSR keeps an int64 indptr
     if (index_width == 4)
-        FB_REQUIRE(M->nnz < (1ll << 31) && M->n < (1ull << 31), "int32 indices cannot hold this matrix");
+        FB_REQUIRE(M->n < (1ull << 31) && (destination == 2 || M->nnz < (1ll << 31)), "int32 indices cannot hold this matrix");
     cudaStream_t st = M->stream;
     const size_t m = M->m, n = M->n;
     const int64_t nnz = M->nnz;
@@ -751,7 +784,9 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         if (tl_path) tl_host[3 * k + 1] = tl_now();
         const int64_t nnz_k = h_nnz[k], off = total;
         total += nnz_k;
-        if (index_width == 4 && total >= (1ll << 31)) throw CudaError{"int32 indices cannot hold this matrix"};
+        // host output in int32: the offsets must fit too.  Reported as "capacity too small" with the entry count,
+        // so that the caller retries with int64 (the device-resident CSR keeps an int64 indptr: no limit there)
+        if (destination == 0 && index_width == 4 && total >= (1ll << 31)) overflow = true;
         if (total > capacity) overflow = true;
         FB_CUDA(cudaStreamWaitEvent(s1, M->sub_events[3 * k + 2], 0));
         bool slot_recorded = false;
@@ -1251,6 +1286,8 @@ int fluxb200_csr_to_host(fluxb200_csr *C, void *indptr, void *indices, void *dat
         FB_REQUIRE(C, "csr is NULL");
         DeviceGuard guard(C->device);
         const size_t es = C->dtype == FLUXB200_F64 ? 8 : 4;
+        FB_REQUIRE(!(indptr && C->index_width == 4 && C->nnz >= (1ll << 31)),
+                   "this slab has 2^31 or more entries: its int32 index dtype cannot hold the row offsets on the host");
         if (indptr) { // int64 on the device; narrowed on the host side if asked
             std::vector<int64_t> ip((size_t)C->m + 1);
             FB_CUDA(cudaMemcpyAsync(ip.data(), C->indptr.p, sizeof(int64_t) * ip.size(), cudaMemcpyDeviceToHost, C->stream));
@@ -1546,7 +1583,7 @@ int fluxb200_mesh_stream(fluxb200_mesh *M, void **stream) {
     });
 }
 
-int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[4]) {
+int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[8]) {
     return guarded([&] {
         FB_REQUIRE(M && out, "NULL argument");
         DeviceGuard guard(M->device);
@@ -1559,6 +1596,10 @@ int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[4]) {
         out[1] = (int64_t)h[2];
         out[2] = (int64_t)h[3];
         out[3] = (int64_t)h[4];
+        out[4] = (int64_t)h[5];
+        out[5] = (int64_t)h[6];
+        out[6] = (int64_t)h[7];
+        out[7] = 0;
     });
 }
 
@@ -1591,6 +1632,9 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->horizon_zone_opt = (int)value;
             M->have_count = false;
             bvh_build(M);
+        } else if (s == "trace_variant") {
+            FB_REQUIRE(value == 1 || value == 2, "trace_variant must be 1 or 2");
+            M->trace_variant_opt = (int)value;
         } else if (s == "blocks_per_sm") {
             FB_REQUIRE(value >= 1 && value <= 8, "blocks_per_sm out of range");
             M->blocks_per_sm = (int)value;

@@ -215,19 +215,36 @@ __device__ __noinline__ bool leaf_occludes_cold(const float4 *tri, Ray r, float 
     return t < tlimit || __float_as_int(p0.w) > target_face;
 }
 
+// r-th (0-based) set bit of w (w has more than r set bits): five popcount halvings, no loop
+__device__ __forceinline__ int nth_set_bit(uint32_t w, int r) {
+    int pos = 0;
+    int c = __popc(w & 0xffffu);
+    if (r >= c) { r -= c; pos = 16; }
+    c = __popc((w >> pos) & 0xffu);
+    if (r >= c) { r -= c; pos += 8; }
+    c = __popc((w >> pos) & 0xfu);
+    if (r >= c) { r -= c; pos += 4; }
+    c = __popc((w >> pos) & 0x3u);
+    if (r >= c) { r -= c; pos += 2; }
+    c = (int)((w >> pos) & 1u);
+    if (r >= c) pos += 1;
+    return pos;
+}
+
 // Generic any-hit traversal with immediate leaf tests (query kernels).
 // With tlimit = t of the target triangle this is "closest hit != target" of the
 // oracle's index-ordered closest-hit definition.  tlimit = +inf, target_leaf =
 // -1: plain occlusion query.
+// `start`: the internal node the walk begins at (0 = root: the whole tree)
 __device__ __forceinline__ bool occluded_anyhit(const BvhView &bvh, const Ray &r, float tlimit,
-                                                int target_leaf, int target_face) {
+                                                int target_leaf, int target_face, int start = 0) {
     if (bvh.nfaces == 0) return false;
     if (bvh.ninternal == 0) // single triangle
         return target_leaf != 0 && leaf_occludes(bvh, r, tlimit, 0, target_face);
     const RayBox rb = make_raybox(r);
     const float tmax = tlimit * 1.000002f;
     int stack[kStackDepth];
-    int sp = 0, node = 0;
+    int sp = 0, node = start;
     while (true) {
         float4 q[6];
         load_node(bvh, node, q);

@@ -132,9 +132,9 @@ def get_form_factor_matrix_device(shape_model, I=None, J=None, eps=None, row_sta
     left in device memory as a :class:`DeviceCsrSlab`."""
     if eps is None:
         eps = config.DEFAULT_EPS
+    # int32 column positions always suffice (n < 2^31); the slab's indptr is int64 on the device, so the
+    # entry count is not limited by the index width
     m, n, _, st = shape_model._ff_assemble_device(I, J, eps, 4)
-    if st.nnz >= 2**31:
-        m, n, _, st = shape_model._ff_assemble_device(I, J, eps, 8)
     h = ctypes.c_void_p()
     _lib.check(_lib.lib().fluxb200_ff_detach_csr(shape_model._handle, ctypes.byref(h)))
     return DeviceCsrSlab(h, shape_model.device, row_start, m_global)

@@ -183,7 +183,19 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             if a.dtype != self.dtype or a.shape != shape:
                 raise RuntimeError(f'face array has dtype/shape {a.dtype}{a.shape}, expected {self.dtype}{shape}')
             arrs.append(a)
-        _lib.check(_lib.lib().fluxb200_mesh_set_face_data(self._handle, *[_lib.ptr(a) for a in arrs]))
+        # Only what differs from what the device already holds is sent: an exact comparison with the
+        # copies kept from the last upload (a memcmp of 28 bytes per face, against a host-to-device
+        # copy + pack kernel + stream synchronisation per query -- the per-block assembly of
+        # CompressedFormFactorMatrix makes 16 / 64 calls on an unchanged shape model).
+        sent = getattr(self, '_sent_face_data', None)
+        send = [a if sent is None or not np.array_equal(a, b, equal_nan=False) else None
+                for a, b in zip(arrs, sent or (None, None, None))]
+        #: bytes of face data the last query really copied to the device (bench.py's h2d count)
+        self.face_bytes_sent_last = sum(a.nbytes for a in send if a is not None)
+        if any(a is not None for a in send):
+            _lib.check(_lib.lib().fluxb200_mesh_set_face_data(self._handle, *[_lib.ptr(a) for a in send]))
+            self._sent_face_data = tuple(a.copy() if s is not None else b
+                                         for a, s, b in zip(arrs, send, sent or (None, None, None)))
 
     # ---- hooks ------------------------------------------------------------------
     def _intersect1(self, x, d):
@@ -262,10 +274,13 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
-    #: largest nnz / (m*n) seen so far: sizes the streaming
-    #: output buffers, with 20 % headroom, so that a retry is the exception
+    #: nnz / (m*n) of this shape model's recent calls (the larger of the last one and 0.9 x the estimate before
+    #: it): sizes the streaming output buffers, with 20 % headroom, so that a retry is the exception.  Per
+    #: instance, and it decays: one dense block must not make every later call page-lock m*n entries.
     _fill_ratio = 0.55
     overflow_retries = 0
+    #: results below this many bytes are copied to ordinary memory and their page-locked block goes back to the arena
+    small_result_bytes = 1 << 20
 
     def _ff_assemble_host(self, I, J, eps, want_row_counts=False, index_dtype=None):
         """Streaming assembly (``fluxb200_ff_assemble``) into page-locked host
@@ -290,10 +305,12 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), isz, 0,
                                         block.ptr + off_ptr, block.ptr + off_idx, block.ptr, cap,
                                         _lib.ptr(counts), ctypes.byref(st))
-            if rc == _lib.OVERFLOW:
+            if rc == _lib.OVERFLOW:      # too many entries for the buffer, or for int32 offsets: st.nnz = the count
                 _lib.arena.discard(block)
                 type(self).overflow_retries += 1
                 cap = int(st.nnz)
+                if index_dtype is not None and np.dtype(index_dtype).itemsize == 4 and cap >= 2**31:
+                    raise RuntimeError('int32 indices cannot hold this matrix')
                 continue
             if rc:
                 _lib.arena.discard(block)
@@ -301,9 +318,12 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             break
         nnz = int(st.nnz)
         if m*n:
-            type(self)._fill_ratio = max(0.02, nnz/(m*n), self._fill_ratio)
+            self._fill_ratio = max(0.02, nnz/(m*n), 0.9*self._fill_ratio)
         data, indices, indptr = _lib.arena.arrays(
             block, [(0, nnz, self.dtype), (off_idx, nnz, idt), (off_ptr, m + 1, idt)])
+        if nnz*(esz + isz) + (m + 1)*isz <= self.small_result_bytes:
+            # many small per-block matrices must not each pin a page-locked block for their lifetime
+            data, indices, indptr = data.copy(), indices.copy(), indptr.copy()
         return m, n, indptr, indices, data, counts, st
 
     def _ff_assemble_device(self, I, J, eps, index_width=4, want_row_counts=False):
@@ -350,10 +370,11 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
 
     def trace_counters(self):
         """Counters of the last assembly's trace launches (``fluxb200_trace_counters``)."""
-        out = np.zeros(4, np.int64)
+        out = np.zeros(8, np.int64)
         _lib.check(_lib.lib().fluxb200_trace_counters(self._handle, _lib.ptr(out)))
         return dict(rays=int(out[0]), batches=int(out[1]), batches_source_skip=int(out[2]),
-                    rays_target_skip=int(out[3]))
+                    rays_target_skip=int(out[3]), rounds=int(out[4]), round_items=int(out[5]),
+                    queue_full_walks=int(out[6]))
 
     def cuda_stream(self):
         s = ctypes.c_void_p()

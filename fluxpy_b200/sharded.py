@@ -15,6 +15,34 @@ import numpy as np
 from . import _lib, config
 
 
+def bind_to_gpu_cpus(device):
+    """Restrict this process -- and the threads it starts afterwards: the library's index-expansion pool, the
+    first touch of the page-locked output arena -- to the CPUs NVML reports as local to GPU ``device`` (its
+    NUMA node).  On a multi-socket box the copy-out of a rank then lands in memory next to its GPU and does not
+    cross the socket interconnect; on a single-node box (or without NVML) it changes nothing.  Returns the CPU
+    list it bound to, or None."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid) if not uuid.startswith('GPU-') else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63)//64)
+        cpus = {64*w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def slab_bounds(m, world_size, weights=None):
     """``starts[world_size+1]`` of the contiguous row slabs (C ABI:
     ``fluxb200_slab_plan``); ``weights`` (e.g. row counts of an earlier pass)

@@ -34,7 +34,7 @@ extern "C" {
 #define FLUXB200_F32 0
 #define FLUXB200_F64 1
 
-#define FLUXB200_ABI_VERSION 6
+#define FLUXB200_ABI_VERSION 7
 
 #define FLUXB200_OK 0
 #define FLUXB200_ERROR 1
@@ -236,13 +236,17 @@ int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
  * "host_expand" (1: fluxb200_ff_assemble ships visibility words to the host and host threads
  * write the column indices; 0: the indices themselves are copied), "host_threads" (0 = automatic),
  * "horizon_skip" (1: the trace kernel skips a face's near zone for rays that clear its horizon --
- * exact, see csrc/horizon.cuh; default 0 until it has been measured on a B200), "horizon_zone"
- * (leaves per near zone, default 1023; the target end of the skip needs zones below the 1024-column chunk). */
+ * exact, see csrc/horizon.cuh; default 1 since it was measured on a B200: trace kernel -30 %), "horizon_zone"
+ * (leaves per near zone, default 1023; the target end of the skip needs zones below the 1024-column chunk),
+ * "trace_variant" (2: trace kernel with a warp-shared traversal queue, csrc/trace2.cuh, the default;
+ * 1: the first-generation kernel with per-lane stacks -- identical results, kept as the A/B reference). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 /* Counters of the last assembly's trace launches: out[0] rays traced (= stats.pairs_tested), and with
  * "horizon_skip" on: out[1] 32-ray batches, out[2] batches walked without the records of the source
- * face's near zone, out[3] rays whose upward walk started at the target's zone node. */
-int fluxb200_trace_counters(fluxb200_mesh *mesh, int64_t out[4]);
+ * face's near zone, out[3] rays whose upward walk started at the target's zone node; "trace_variant" 2:
+ * out[4] traversal rounds, out[5] items those rounds processed (32 per round = every lane busy),
+ * out[6] subtrees / triangles a lane handled itself because a queue was full; out[7] reserved. */
+int fluxb200_trace_counters(fluxb200_mesh *mesh, int64_t out[8]);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,29 @@ typedef struct oracle_scene {
 
 /* --- the Pluecker test ---------------------------------------------------- */
 
+/* STUDY VARIANTS (tests/test_oracle_golden.py::test_embree_arithmetic_variants_*): the contract -- what the CUDA
+ * path is compared with bit for bit -- is variant (0, 0).  Real Embree differs from it in two places that no
+ * reference test pins: the hit distance is T * rcp(den) with rcp = the hardware's 12-bit reciprocal estimate plus
+ * one Newton step (embree3 common/math/math.h, common/simd/vfloat4_sse2.h), not an exact division; and among
+ * equal-t hits the winner depends on Embree's BVH order, not on the face index.  These switches let a test bound
+ * what either can change: g_tmode 1 = r*(2 - r*den) (SSE2 build), 2 = r + r*(1 - den*r) with FMA (AVX2 build);
+ * g_tie 1 = among equal t the SMALLEST index wins. */
+#include <immintrin.h>
+static int g_tmode = 0, g_tie = 0;
+void oracle_set_study_variant(int tmode, int tie) {
+    g_tmode = tmode;
+    g_tie = tie;
+}
+static inline float hit_distance(float T, float den) {
+    if (g_tmode == 0) return T / den;
+    const __m128 a = _mm_set_ss(den);
+    const __m128 r = _mm_rcp_ss(a);
+    float rcp;
+    if (g_tmode == 1) rcp = _mm_cvtss_f32(_mm_mul_ss(r, _mm_sub_ss(_mm_set_ss(2.0f), _mm_mul_ss(r, a))));
+    else rcp = _mm_cvtss_f32(_mm_add_ss(r, _mm_mul_ss(r, _mm_fnmadd_ss(a, r, _mm_set_ss(1.0f)))));
+    return rcp * T;
+}
+
 static inline float msubf(float a, float b, float c) { return fmaf(a, b, -c); } /* a*b - c */
 static inline float dot3f(const float a[3], const float b[3]) {
     return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2]));
@@ -135,7 +158,7 @@ static inline int pluecker_hit(const float org[3], const float dir[3], float tne
     const float Tn = dot3f(v0, Ng);
     const float T = Tn + Tn;
     if (den == 0.0f) return 0;
-    const float t = T / den;
+    const float t = hit_distance(T, den);
     if (!(tnear <= t && t <= tfar)) return 0;
     *t_out = t;
     return 1;
@@ -152,6 +175,7 @@ static void closest_hit_brute(const oracle_scene *s, const float org[3], const f
     for (size_t k = 0; k < s->nf; ++k) {
         float t;
         if (pluecker_hit(org, dir, tnear, best, s->tri + 9 * k, &t)) {
+            if (g_tie && id != ORACLE_INVALID_ID && t == best) continue; /* study variant: the first of equal t stays */
             best = t;
             id = (uint32_t)k;
         }
@@ -279,7 +303,7 @@ static void closest_hit_bvh(const oracle_scene *s, const float org[3], const flo
                 /* same winner as the index-ordered brute force: smaller t, or
                  * equal t and larger index */
                 if (pluecker_hit(org, dir, tnear, best, s->tri + 9 * (size_t)k, &t)) {
-                    if (t < best || id == ORACLE_INVALID_ID || k > id) {
+                    if (t < best || id == ORACLE_INVALID_ID || (g_tie ? k < id : k > id)) {
                         best = t;
                         id = k;
                     }

@@ -61,6 +61,7 @@ def lib():
         f.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz, ctypes.c_double, i32, i32]
         getattr(L, 'oracle_face_geometry_' + sfx).argtypes = [vp, vp, sz, vp, vp, vp]
     L.oracle_team_size.argtypes = [i32]
+    L.oracle_set_study_variant.argtypes = [i32, i32]
     L.oracle_team_size.restype = i32
     L.oracle_ff_nnz.restype = ctypes.c_int64
     L.oracle_ff_nnz.argtypes = [vp]
@@ -100,6 +101,12 @@ def face_geometry(V, F):
 def team_size(nthreads=0):
     """OpenMP threads a region asked for ``nthreads`` (0 = default) really gets."""
     return int(lib().oracle_team_size(int(nthreads)))
+
+
+def set_study_variant(tmode=0, tie=0):
+    """Study switches of ff_oracle.c (hit distance as Embree's rcp + Newton step, equal-t winner by smallest
+    index).  (0, 0) is the contract; anything else is for the sensitivity tests only."""
+    lib().oracle_set_study_variant(int(tmode), int(tie))
 
 
 class OracleScene:

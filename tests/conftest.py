@@ -37,6 +37,18 @@ def pytest_configure(config):
         shape.CudaTrimeshShapeModel.__init__ = init_with_horizon
 
 
+    variant = os.environ.get('FLUXB200_TEST_VARIANT')
+    if variant:
+        # the same for the trace kernel's generation (1: per-lane stacks, 2: warp-shared queue, the default)
+        from fluxpy_b200 import shape
+        prev_init = shape.CudaTrimeshShapeModel.__init__
+
+        def init_with_variant(self, *args, **kwargs):
+            prev_init(self, *args, **kwargs)
+            self.set_option('trace_variant', int(variant))
+        shape.CudaTrimeshShapeModel.__init__ = init_with_variant
+
+
 # gpu-tier tests that hand torch CUDA tensors (device pointers) to the library or need NCCL: no emulator run
 NEEDS_REAL_DEVICE = ('test_device_resident_radiosity_and_steady_state', 'test_block_extraction_and_lowrank_feed',
                      'test_two_rank_sharded_assembly_and_solve', 'test_ingersoll_device_resident_solver')

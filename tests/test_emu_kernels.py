@@ -8,8 +8,9 @@ vectors) run here unchanged, on the kernels' real source.  This is test infrastr
 no switch for it and never loads it; what it proves is the kernels' logic and warp synchronisation, not
 their speed, and not anything that depends on the hardware's memory model.
 
-The second run repeats the subset with the trace kernel's horizon skip forced on (FLUXB200_TEST_HORIZON),
-the variant that is off by default until it has been measured on a B200.
+The default path is the second-generation trace kernel (csrc/trace2.cuh: warp-shared traversal queue) with the
+horizon skip on.  The second run repeats the subset with a small zone size (FLUXB200_TEST_HORIZON=16: both ends
+of the skip exercised on these small meshes), the third with the first-generation kernel and the skip off.
 """
 import os
 import subprocess
@@ -66,6 +67,16 @@ def test_gpu_parity_subset_on_the_emulator_with_horizon_skip(emu_lib):
     run_gpu_subset({'FLUXB200_TEST_HORIZON': '16'})
 
 
+def test_gpu_parity_subset_on_the_emulator_first_generation_kernel(emu_lib):
+    """The quick crater / sphere cases with the first-generation trace kernel (per-lane stacks) and the skip
+    off: the A/B reference of trace2.cuh stays bit-identical to the oracle too."""
+    env = dict(os.environ, FLUXB200_TEST_EMU='1', FLUXB200_TEST_VARIANT='1', FLUXB200_TEST_HORIZON='0')
+    out = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_parity.py', '-m', 'gpu', '-q', '-x', '-k',
+                          'test_sphere_fixtures or (test_crater_vs_oracle_and_golden and not case2) or test_edge_cases',
+                          '-p', 'no:cacheprovider'], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0 and ' passed' in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
 HORIZON_SCRIPT = r'''
 import sys, json, numpy as np
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + '/tools/simt')
@@ -87,6 +98,7 @@ for (n, seed, scale, zone, nrows, flip) in [(40, 2, 1.0, 64, 0, False), (72, 0, 
     nf = len(F)
     I = None if nrows == 0 else np.linspace(0, nf - 1, nrows).astype(np.int64)
     sm = fluxpy_b200.CudaTrimeshShapeModel(V, F, N.copy())
+    sm.set_option('horizon_skip', 0)
     F0 = fluxpy_b200.get_form_factor_matrix(sm, I)
     sm.set_option('horizon_zone', zone)
     sm.set_option('horizon_skip', 1)

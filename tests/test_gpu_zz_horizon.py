@@ -30,6 +30,7 @@ def test_horizon_skip_full_matrix_vs_oracle(mods, zone, dtype):
     N[::5] *= -1                                   # user-flipped normals: the horizons follow the CURRENT N
     sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
     om = mods['oracle'].OracleShapeModel(V, F, N=N.copy())
+    sm.set_option('horizon_skip', 0)               # (the skip is the default since round 2)
     off = mods['ff'].get_form_factor_matrix(sm)
     sm.set_option('horizon_zone', zone)
     sm.set_option('horizon_skip', 1)
@@ -51,6 +52,7 @@ def test_horizon_skip_sampled_rows_at_scale(mods, scale):
     V = (V*np.float32(scale)).astype(np.float32)
     sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
     I = np.linspace(0, sm.num_faces - 1, 192).astype(np.int64)
+    sm.set_option('horizon_skip', 0)
     off = mods['ff'].get_form_factor_matrix(sm, I)
     sm.set_option('horizon_skip', 1)
     on = mods['ff'].get_form_factor_matrix(sm, I)

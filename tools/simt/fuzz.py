@@ -154,10 +154,13 @@ def main():
                     sm.set_option(name, opts[name])
         FO = oracle.get_form_factor_matrix(om, I, J, eps)
         FO.sort_indices()
+        variant = int(rng.choice([1, 2, 2]))     # trace kernel generation (2 = warp-shared queue, the default)
+        sm.set_option('trace_variant', variant)
+        opts['trace_variant'] = variant
         for hor in (0, 1):
+            sm.set_option('horizon_skip', hor)
             if hor:
                 sm.set_option('horizon_zone', zone)
-                sm.set_option('horizon_skip', 1)
             FF = fluxpy_b200.get_form_factor_matrix(sm, I, J, eps)
             FF.sort_indices()
             ok = (FF.shape == FO.shape and FF.nnz == FO.nnz and np.array_equal(FF.indptr, FO.indptr)

@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, 'libfluxb200.so')
+# (FLUXB200_SO: another build of the same library, e.g. a tuning variant made by `make -C csrc VARIANT=...`)
+SO_PATH = os.environ.get('FLUXB200_SO') or os.path.join(_HERE, 'libfluxb200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 F32, F64 = 0, 1

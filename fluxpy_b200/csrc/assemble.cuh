@@ -725,16 +725,19 @@ template <class T> struct FillArgs {
 };
 
 // One CTA = 8 consecutive rows (one per warp) x one segment of the column groups (blockIdx.y; the
-// row's entry count before the segment comes from K6a's per-group counts).  A group of 1024 columns is
-// taken in two halves of 512: the CTA gathers P, N, A of the half's columns into shared memory once --
+// row's entry count before the segment comes from K6a's per-group counts).  Per group of 1024 columns
+// the CTA gathers P, N, A of the columns into shared memory once --
 // ALREADY CONVERTED TO DOUBLE (round 1 converted per stored entry: 13 F2F per entry kept the XU pipe 53 %
 // busy and the kernel at 20 % of the HBM write bandwidth) -- the gather through `cols` and the L2 reads
 // are shared by the 8 rows; then every warp emits its row's entries of the half, two entries per lane
 // and iteration (independent fp64 chains).
 constexpr int kFillGroup = 1024;
-constexpr int kFillHalf = 512;
-struct __align__(16) EmitCol { double px, py, pz, area, nx, ny, nz, pad; }; // 64 B per staged column
-template <class T> constexpr size_t emit_smem_bytes() { return sizeof(EmitCol) * kFillHalf; }
+constexpr int kFillHalf = 1024; // columns staged at a time (= one group; 512 halved the lanes of the bit expansion)
+// staged columns, structure of arrays: px[512] py[512] pz[512] area[512] nx[512] ny[512] nz[512] (doubles).
+// (An array of 64-byte structs put every lane's 16-byte pieces on two bank groups: 16-way conflicts, 5.1 ms per
+// slab against 2.3 ms for the round-1 kernel -- profiles/r02c_*.)
+struct EmitCol { double px, py, pz, area, nx, ny, nz; };
+template <class T> constexpr size_t emit_smem_bytes() { return sizeof(double) * 7 * kFillHalf; }
 
 // F_ij = max(0, n_i.d) max(0, -n_j.d) A_j / (pi r^4), d = p_j - p_i, in fp64 from the model-dtype inputs
 // (form_factors.py:46-47 evaluated directly, :62-64); the operation order of numerator<T>() above
@@ -754,7 +757,11 @@ __device__ __forceinline__ double form_factor_value(double pix, double piy, doub
 template <class T>
 __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
-    EmitCol *col_s = reinterpret_cast<EmitCol *>(stage_raw);
+    double *col_s = reinterpret_cast<double *>(stage_raw);
+    auto staged = [&](int c) {
+        return EmitCol{col_s[c], col_s[kFillHalf + c], col_s[2 * kFillHalf + c], col_s[3 * kFillHalf + c],
+                       col_s[4 * kFillHalf + c], col_s[5 * kFillHalf + c], col_s[6 * kFillHalf + c]};
+    };
     __shared__ uint16_t list_s[kFillWarps][kFillHalf];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * kFillWarps + warp;
@@ -777,31 +784,37 @@ __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A)
     const Real4<T> Pi = load_real4<T>(A.faceP + i), Ni = load_real4<T>(A.faceN + i);
     const double pix = (double)Pi.x, piy = (double)Pi.y, piz = (double)Pi.z;
     const double nix = (double)Ni.x, niy = (double)Ni.y, niz = (double)Ni.z;
-    for (int gh = 2 * g_begin; gh < 2 * g_end; ++gh) {
-        const int q0 = gh * kFillHalf; // first column of this half
-        if (q0 >= A.n) break;          // (uniform: the second half of the last group may be empty)
+    constexpr int kTilesPerGroup = kFillGroup / kFillHalf, kTileWords = kFillHalf / 32;
+    for (int gh = kTilesPerGroup * g_begin; gh < kTilesPerGroup * g_end; ++gh) {
+        const int q0 = gh * kFillHalf; // first column of this tile
+        if (q0 >= A.n) break;          // (uniform: the last tile of the last group may be empty)
         __syncthreads(); // the previous half's columns are no longer read
         for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
             const int q = q0 + c;
             if (q < A.n) {
                 const int j = A.cols[q];
                 const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
-                col_s[c] = EmitCol{(double)Pj.x, (double)Pj.y, (double)Pj.z, (double)Pj.w,
-                                   (double)Nj.x, (double)Nj.y, (double)Nj.z, 0.0};
+                col_s[c] = (double)Pj.x;
+                col_s[kFillHalf + c] = (double)Pj.y;
+                col_s[2 * kFillHalf + c] = (double)Pj.z;
+                col_s[3 * kFillHalf + c] = (double)Pj.w;
+                col_s[4 * kFillHalf + c] = (double)Nj.x;
+                col_s[5 * kFillHalf + c] = (double)Nj.y;
+                col_s[6 * kFillHalf + c] = (double)Nj.z;
             }
         }
         __syncthreads();
         if (!live) continue;
-        const int wi = gh * 16 + lane;
-        uint32_t word = (lane < 16 && wi < A.nwords) ? jb[wi] : 0u;
+        const int wi = gh * kTileWords + lane;
+        uint32_t word = (lane < kTileWords && wi < A.nwords) ? jb[wi] : 0u;
         const int c = __popc(word);
         int incl = c;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
+        for (int o = 1; o < kTileWords; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 15);
+        const int total = __shfl_sync(0xffffffffu, incl, kTileWords - 1);
         if (total == 0) continue;
         int p = incl - c;
         while (word) { // ascending positions of my word's set bits
@@ -813,8 +826,8 @@ __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A)
             const int e1 = e + 32;
             const bool two = e1 < total;
             const int c0 = (int)list_s[warp][e], c1 = two ? (int)list_s[warp][e1] : c0;
-            const double v0 = form_factor_value(pix, piy, piz, nix, niy, niz, col_s[c0]);
-            const double v1 = form_factor_value(pix, piy, piz, nix, niy, niz, col_s[c1]);
+            const double v0 = form_factor_value(pix, piy, piz, nix, niy, niz, staged(c0));
+            const double v1 = form_factor_value(pix, piy, piz, nix, niy, niz, staged(c1));
             // streaming stores: the CSR is written once and must not push the mesh and BVH, which a
             // concurrently running trace kernel lives on, out of L2
             const int64_t dst = off + e;
@@ -927,8 +940,8 @@ __global__ void col_gather_kernel(const uint32_t *__restrict__ pos, const int *_
     rank_of_pos[q] = s;
 }
 
-// interleave host-side P (nf x 3), N (nf x 3), A (nf) into the packed arrays; *changed is set when a
-// P or N value differs from the one it replaces (the horizons of horizon.cuh depend on them)
+// interleave host-side P (nf x 3), N (nf x 3), A (nf) into the packed arrays; *changed gets bit 0 when a
+// P or N value differs from the one it replaces (the horizons of horizon.cuh depend on them), bit 1 for A
 template <class T>
 __global__ void pack_face_kernel(const T *__restrict__ P, const T *__restrict__ N, const T *__restrict__ A,
                                  int nf, Real4<T> *__restrict__ faceP, Real4<T> *__restrict__ faceN,
@@ -943,7 +956,11 @@ __global__ void pack_face_kernel(const T *__restrict__ P, const T *__restrict__ 
         faceP[f].y = y;
         faceP[f].z = z;
     }
-    if (A) faceP[f].w = A[f];
+    bool adiff = false;
+    if (A) {
+        adiff = !(faceP[f].w == A[f]);
+        faceP[f].w = A[f];
+    }
     if (N) {
         const T x = N[3 * (size_t)f], y = N[3 * (size_t)f + 1], z = N[3 * (size_t)f + 2];
         diff = diff || !(faceN[f].x == x && faceN[f].y == y && faceN[f].z == z);
@@ -952,7 +969,8 @@ __global__ void pack_face_kernel(const T *__restrict__ P, const T *__restrict__ 
         faceN[f].z = z;
         faceN[f].w = (T)0;
     }
-    if (diff) *changed = 1;
+    if (diff) atomicOr(reinterpret_cast<unsigned *>(changed), 1u);  // P or N: horizons and prepared column sets are stale
+    if (adiff) atomicOr(reinterpret_cast<unsigned *>(changed), 2u); // A: the prepared column sets only
 }
 
 template <class T>

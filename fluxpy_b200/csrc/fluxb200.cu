@@ -26,6 +26,22 @@ thread_local std::string g_last_error;
 }
 using namespace fluxb200;
 
+// One prepared column set J of an assembly: the columns sorted by leaf (Morton) position and everything gathered
+// in that order.  The handle keeps the last few (LRU): CompressedFormFactorMatrix assembles 16 / 64 root blocks
+// over 4 / 8 column parts (reference src/flux/compressed_form_factors.py:551-567), and the sort + gathers of a
+// part are the same for every row part.
+struct ColSet {
+    DevBuf cols, colP, colN, col_face, col_leaf, rank_of_pos, chunk_info, colH;
+    std::vector<int64_t> key; // the caller's J (empty when arange)
+    bool arange = false, valid = false;
+    size_t n = 0;
+    uint64_t face_epoch = 0, tree_epoch = 0, used = 0;
+    void release() {
+        for (DevBuf *b : {&cols, &colP, &colN, &col_face, &col_leaf, &rank_of_pos, &chunk_info, &colH}) b->release();
+        valid = false;
+    }
+};
+
 struct fluxb200_mesh {
     int device = 0;
     int dtype = FLUXB200_F32;
@@ -51,16 +67,24 @@ struct fluxb200_mesh {
     int horizon_skip_opt = 1;
     int horizon_zone_opt = 1023; // Z: leaves per near zone (below the 1024-column chunk: the upward walk must end above every zone)
     bool hz_dirty = true;       // P, N or the tree changed since the horizons were computed
-    DevBuf hz, zone_node, zone_up, colH;
+    DevBuf hz, zone_node, zone_up;
     // trace kernel generation: 2 = warp-shared traversal queue (trace2.cuh), 1 = per-lane stacks (assemble.cuh)
     int trace_variant_opt = 2;
-    DevBuf chunk_info, lost; // lost: [0] count, then (row, column) pairs of rays for resolve_lost_kernel
+    DevBuf lost; // lost: [0] count, then (row, column) pairs of rays for resolve_lost_kernel
     float ms_build = 0.f;
     float scene_h[7] = {};
 
     // per-call state
-    DevBuf rows, cols, ckeys, cvals, colP, colN, col_face, col_leaf, rank_of_pos, bits, row_counts,
-        counts64, indptr, indptr32, tested, out_data, out_indices, qtmp, qout, jbits;
+    DevBuf rows, ckeys, cvals, bits, row_counts, counts64, indptr, indptr32, tested, out_data, out_indices, qtmp,
+        qout, jbits;
+    // prepared column sets: [0] is the scratch set of the query kernels, [1..] the LRU cache of assemblies
+    std::vector<std::unique_ptr<ColSet>> colsets;
+    ColSet *cs = nullptr;          // the set the current call works on
+    uint64_t face_epoch = 1;       // bumped when P or N changes on the device
+    uint64_t tree_epoch = 1;       // bumped when the tree (or an option baked into per-column data) changes
+    uint64_t use_clock = 0;
+    int colset_cache_opt = 8;      // cached column sets (0: prepare every call)
+    int64_t colset_hits = 0, colset_misses = 0;
     // streaming assembly (double-buffered sub-slabs, second stream for fill + D2H)
     cudaStream_t copy_stream = nullptr; // fill kernels
     cudaStream_t d2h_stream = nullptr;  // copy-out (its own stream: fill(k+1) must not queue behind D2H(k))
@@ -249,6 +273,7 @@ void bvh_build(fluxb200_mesh *M) {
                                                            M->node_range.as<int2>());
     }
     M->hz_dirty = true;
+    ++M->tree_epoch; // every prepared column set is stale
     if (M->horizon_skip_opt) {
         M->zone_node.reserve(sizeof(int) * n);
         M->zone_up.reserve(sizeof(int) * n);
@@ -299,11 +324,11 @@ template <class T> void set_face_data(fluxb200_mesh *M, const void *P, const voi
         P ? dP : nullptr, N ? dN : nullptr, A ? dA : nullptr, (int)nf, M->faceP.as<Real4<T>>(),
         M->faceN.as<Real4<T>>(), changed);
     FB_CUDA(cudaGetLastError());
-    int h_changed = 1;
-    if (M->horizon_skip_opt) // the horizons are recomputed only when P or N really changed
-        FB_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int h_changed = 1; // derived data (horizons, prepared column sets) is redone only when P or N really changed
+    FB_CUDA(cudaMemcpyAsync(&h_changed, changed, sizeof(int), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
-    if (h_changed) M->hz_dirty = true;
+    if (h_changed & 1) M->hz_dirty = true;
+    if (h_changed) ++M->face_epoch; // (the areas travel in the gathered colP.w: a new A invalidates the copies too)
 }
 
 template <class T> void get_face_data(fluxb200_mesh *M, void *P, void *N, void *A) {
@@ -321,14 +346,69 @@ template <class T> void get_face_data(fluxb200_mesh *M, void *P, void *N, void *
     FB_CUDA(cudaStreamSynchronize(st));
 }
 
-void upload_index_sets(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n) {
-    FB_REQUIRE(m < (1ull << 31) && n < (1ull << 31), "index sets must have fewer than 2^31 entries");
-    const std::vector<int> rows = to_i32(I, m, M->nf, "I"), cols = to_i32(J, n, M->nf, "J");
+ColSet *scratch_colset(fluxb200_mesh *M) {
+    if (M->colsets.empty()) M->colsets.emplace_back(new ColSet());
+    return M->colsets[0].get();
+}
+
+void upload_rows(fluxb200_mesh *M, const int64_t *I, size_t m) {
+    FB_REQUIRE(m < (1ull << 31), "index sets must have fewer than 2^31 entries");
+    const std::vector<int> rows = to_i32(I, m, M->nf, "I");
     M->rows.reserve(sizeof(int) * std::max<size_t>(m, 1));
-    M->cols.reserve(sizeof(int) * std::max<size_t>(n, 1));
     if (m) FB_CUDA(cudaMemcpyAsync(M->rows.p, rows.data(), sizeof(int) * m, cudaMemcpyHostToDevice, M->stream));
-    if (n) FB_CUDA(cudaMemcpyAsync(M->cols.p, cols.data(), sizeof(int) * n, cudaMemcpyHostToDevice, M->stream));
-    FB_CUDA(cudaStreamSynchronize(M->stream)); // the host vectors go out of scope
+    FB_CUDA(cudaStreamSynchronize(M->stream)); // the host vector goes out of scope
+}
+
+void upload_cols(fluxb200_mesh *M, ColSet *C, const int64_t *J, size_t n) {
+    FB_REQUIRE(n < (1ull << 31), "index sets must have fewer than 2^31 entries");
+    const std::vector<int> cols = to_i32(J, n, M->nf, "J");
+    C->cols.reserve(sizeof(int) * std::max<size_t>(n, 1));
+    if (n) FB_CUDA(cudaMemcpyAsync(C->cols.p, cols.data(), sizeof(int) * n, cudaMemcpyHostToDevice, M->stream));
+    FB_CUDA(cudaStreamSynchronize(M->stream));
+}
+
+// query kernels: both index sets, columns into the scratch set (never cached)
+void upload_index_sets(fluxb200_mesh *M, const int64_t *I, size_t m, const int64_t *J, size_t n) {
+    ColSet *C = scratch_colset(M);
+    C->valid = false;
+    M->cs = C;
+    upload_rows(M, I, m);
+    upload_cols(M, C, J, n);
+}
+
+// The prepared column set for J: a cached one (same J, same face data, same tree) or the least recently used
+// entry, to be refilled by the caller (returns false).
+bool find_colset(fluxb200_mesh *M, const int64_t *J, size_t n) {
+    scratch_colset(M);
+    const size_t cap = (size_t)std::max(M->colset_cache_opt, 1);
+    ColSet *lru = nullptr;
+    for (size_t k = 1; k < M->colsets.size(); ++k) {
+        ColSet *C = M->colsets[k].get();
+        if (M->colset_cache_opt > 0 && C->valid && C->n == n && C->face_epoch == M->face_epoch &&
+            C->tree_epoch == M->tree_epoch && C->arange == (J == nullptr) &&
+            (J == nullptr || memcmp(C->key.data(), J, sizeof(int64_t) * n) == 0)) {
+            C->used = ++M->use_clock;
+            M->cs = C;
+            ++M->colset_hits;
+            return true;
+        }
+        if (!lru || C->used < lru->used) lru = C;
+    }
+    ++M->colset_misses;
+    if (M->colsets.size() < cap + 1) {
+        M->colsets.emplace_back(new ColSet());
+        lru = M->colsets.back().get();
+    }
+    lru->valid = false;
+    lru->n = n;
+    lru->arange = J == nullptr;
+    if (J) lru->key.assign(J, J + n);
+    else lru->key.clear();
+    lru->face_epoch = M->face_epoch;
+    lru->tree_epoch = M->tree_epoch;
+    lru->used = ++M->use_clock;
+    M->cs = lru;
+    return false;
 }
 
 // ---- per-call pieces shared by the two-phase and the streaming assembly ---------
@@ -349,21 +429,36 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
     M->eps = eps;
     M->nwords = (int)ceil_div((int64_t)n, 32);
     int launches = 0;
-    upload_index_sets(M, I, m, J, n);
-    M->stats.h2d_bytes = (int64_t)(sizeof(int) * (m + n));
+    upload_rows(M, I, m);
+    M->stats.h2d_bytes = (int64_t)(sizeof(int) * m);
     M->tested.reserve(sizeof(unsigned long long) * 8); // [0] rays, [1] work-unit counter, [2..4] horizon-skip counters
     FB_CUDA(cudaMemsetAsync(M->tested.p, 0, sizeof(unsigned long long) * 8, st));
+    const bool hor = M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0;
+    if (hor && M->hz_dirty && m && n) { // per-face horizons from the shape model's CURRENT P, N (before the lookup:
+        const int nf = (int)M->nf;      // a set cached under this face epoch must see these horizons)
+        M->hz.reserve(sizeof(float2) * (size_t)nf);
+        horizon_kernel<T><<<blocks_for((int64_t)nf * 32, 256), 256, 0, st>>>(
+            nf, M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->face_leaf.as<int>(),
+            M->zone_node.as<int>(), M->node_range.as<int2>(), M->tri.as<float4>(), horizon_pert(M),
+            M->hz.as<float2>());
+        M->hz_dirty = false;
+        ++launches;
+    }
+    if (find_colset(M, J, n)) return launches; // sorted, gathered and annotated by an earlier call: nothing to do
+    ColSet *C = M->cs;
+    upload_cols(M, C, J, n);
+    M->stats.h2d_bytes += (int64_t)(sizeof(int) * n);
     if (m && n) {
         M->ckeys.reserve(sizeof(uint64_t) * n);
         M->cvals.reserve(sizeof(uint32_t) * n);
-        M->colP.reserve(sizeof(Real4<T>) * n);
-        M->colN.reserve(sizeof(Real4<T>) * n);
-        M->col_face.reserve(sizeof(int) * n);
-        M->col_leaf.reserve(sizeof(int) * n);
-        M->rank_of_pos.reserve(sizeof(int) * n);
+        C->colP.reserve(sizeof(Real4<T>) * n);
+        C->colN.reserve(sizeof(Real4<T>) * n);
+        C->col_face.reserve(sizeof(int) * n);
+        C->col_leaf.reserve(sizeof(int) * n);
+        C->rank_of_pos.reserve(sizeof(int) * n);
         const int B = 256;
         const int l0 = M->sorter.launches;
-        col_keys_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(M->cols.as<int>(), (int)n,
+        col_keys_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(C->cols.as<int>(), (int)n,
                                                                  M->face_leaf.as<int>(),
                                                                  M->ckeys.as<uint64_t>(),
                                                                  M->cvals.as<uint32_t>());
@@ -371,39 +466,30 @@ template <class T> int prepare_call(fluxb200_mesh *M, const int64_t *I, size_t m
         while ((1ull << bits) < M->nf) ++bits;
         M->sorter.sort(M->ckeys.as<uint64_t>(), M->cvals.as<uint32_t>(), (int)n, bits, st);
         col_gather_kernel<T><<<blocks_for((int64_t)n, B), B, 0, st>>>(
-            M->cvals.as<uint32_t>(), M->cols.as<int>(), (int)n, M->face_leaf.as<int>(),
-            M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->colP.as<Real4<T>>(),
-            M->colN.as<Real4<T>>(), M->col_face.as<int>(), M->col_leaf.as<int>(),
-            M->rank_of_pos.as<int>());
+            M->cvals.as<uint32_t>(), C->cols.as<int>(), (int)n, M->face_leaf.as<int>(),
+            M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), C->colP.as<Real4<T>>(),
+            C->colN.as<Real4<T>>(), C->col_face.as<int>(), C->col_leaf.as<int>(),
+            C->rank_of_pos.as<int>());
         FB_CUDA(cudaGetLastError());
         launches += 2 + (M->sorter.launches - l0);
         { // per-chunk data shared by every row (trace2.cuh)
             const int nchunks = (int)ceil_div((int64_t)n, kChunkCols);
-            M->chunk_info.reserve(sizeof(float4) * 3 * (size_t)nchunks);
+            C->chunk_info.reserve(sizeof(float4) * 3 * (size_t)nchunks);
             chunk_info_kernel<T><<<blocks_for((int64_t)nchunks * 32, B), B, 0, st>>>(
-                M->colP.as<Real4<T>>(), M->col_leaf.as<int>(), (int)n, nchunks, M->leaf_up.as<int>(),
-                M->node_up.as<int>(), M->node_range.as<int2>(), M->ninternal, M->chunk_info.as<float4>());
+                C->colP.as<Real4<T>>(), C->col_leaf.as<int>(), (int)n, nchunks, M->leaf_up.as<int>(),
+                M->node_up.as<int>(), M->node_range.as<int2>(), M->ninternal, C->chunk_info.as<float4>());
             FB_CUDA(cudaGetLastError());
             ++launches;
         }
-        if (M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0) {
-            const int nf = (int)M->nf;
-            if (M->hz_dirty) { // from the shape model's CURRENT P, N
-                M->hz.reserve(sizeof(float2) * (size_t)nf);
-                horizon_kernel<T><<<blocks_for((int64_t)nf * 32, 256), 256, 0, st>>>(
-                    nf, M->faceP.as<Real4<T>>(), M->faceN.as<Real4<T>>(), M->face_leaf.as<int>(),
-                    M->zone_node.as<int>(), M->node_range.as<int2>(), M->tri.as<float4>(), horizon_pert(M),
-                    M->hz.as<float2>());
-                M->hz_dirty = false;
-                ++launches;
-            }
-            M->colH.reserve(sizeof(float4) * n);
+        if (hor) {
+            C->colH.reserve(sizeof(float4) * n);
             col_horizon_kernel<<<blocks_for((int64_t)n, B), B, 0, st>>>(
-                M->col_face.as<int>(), M->col_leaf.as<int>(), (int)n, M->hz.as<float2>(), M->zone_node.as<int>(),
-                M->zone_up.as<int>(), M->colH.as<float4>());
+                C->col_face.as<int>(), C->col_leaf.as<int>(), (int)n, M->hz.as<float2>(), M->zone_node.as<int>(),
+                M->zone_up.as<int>(), C->colH.as<float4>());
             FB_CUDA(cudaGetLastError());
             ++launches;
         }
+        C->valid = true;
     }
     return launches;
 }
@@ -419,10 +505,10 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     A.node_up = M->node_up.as<int>();
     A.leaf_up = M->leaf_up.as<int>();
     A.node_range = M->node_range.as<int2>();
-    A.colP = M->colP.as<Real4<T>>();
-    A.colN = M->colN.as<Real4<T>>();
-    A.col_face = M->col_face.as<int>();
-    A.col_leaf = M->col_leaf.as<int>();
+    A.colP = M->cs->colP.as<Real4<T>>();
+    A.colN = M->cs->colN.as<Real4<T>>();
+    A.col_face = M->cs->col_face.as<int>();
+    A.col_leaf = M->cs->col_leaf.as<int>();
     A.m = (int)mr;
     A.n = (int)M->n;
     A.nwords = M->nwords;
@@ -441,10 +527,10 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
     const bool hor = M->horizon_skip_opt && M->ninternal > 0 && M->ntop == 0;
     A.hz = hor ? M->hz.as<float2>() : nullptr;
     A.zone_node = hor ? M->zone_node.as<int>() : nullptr;
-    A.colH = hor ? M->colH.as<float4>() : nullptr;
+    A.colH = hor ? M->cs->colH.as<float4>() : nullptr;
     A.zone_leaves = M->horizon_zone_opt;
     A.pert = horizon_pert(M);
-    A.chunk_info = M->chunk_info.as<float4>();
+    A.chunk_info = M->cs->chunk_info.as<float4>();
     A.nchunks = (int)ceil_div((int64_t)M->n, kChunkCols);
     FB_REQUIRE((int64_t)mr * A.nchunks < (1ll << 32) - 65536, "too many work units for one launch");
     const size_t smem = sizeof(float4) * 6 * (size_t)M->ntop;
@@ -471,6 +557,9 @@ template <class T> void launch_trace(fluxb200_mesh *M, size_t row0, size_t mr, u
         FB_CUDA(cudaMemsetAsync(A.lost_count, 0, sizeof(unsigned), st));
         FB_CUDA(cudaFuncSetAttribute(trace2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)trace2_smem_bytes()));
+        // shared memory for exactly the resident CTAs; the rest of the 256 KB stays L1 (BVH records, triangles)
+        const int carve = (int)std::min<size_t>(100, ((size_t)M->blocks_per_sm * (trace2_smem_bytes() + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        FB_CUDA(cudaFuncSetAttribute(trace2_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         trace2_kernel<T><<<grid, kTraceThreads, trace2_smem_bytes(), st>>>(A);
         resolve_lost_kernel<T><<<M->num_sms * 4, 128, 0, st>>>(A);
     } else if (M->ntop > 0) trace_kernel<T, true><<<grid, kTraceThreads, smem, st>>>(A);
@@ -510,7 +599,7 @@ template <class T> void launch_fill(fluxb200_mesh *M, size_t row0, size_t mr, co
     if (R < 2) R = budget_full / row_bytes;
     if (M->fill_rows_opt > 0) R = std::min<size_t>(budget_full / row_bytes, (size_t)M->fill_rows_opt); // A/B and tests
     if (M->fill_rows_opt < 0) R = 0;
-    const int *rank = M->rank_of_pos.as<int>();
+    const int *rank = M->cs->rank_of_pos.as<int>();
     if (R >= 8) launch_unpermute<8, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 8 * row_bytes, st);
     else if (R >= 4) launch_unpermute<4, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 4 * row_bytes, st);
     else if (R >= 2) launch_unpermute<2, true>(bits, rank, (int)mr, n, nwords, jbits, gcount, 2 * row_bytes, st);
@@ -521,7 +610,7 @@ template <class T> void launch_fill(fluxb200_mesh *M, size_t row0, size_t mr, co
     A.faceP = M->faceP.as<Real4<T>>();
     A.faceN = M->faceN.as<Real4<T>>();
     A.rows = M->rows.as<int>() + row0;
-    A.cols = M->cols.as<int>();
+    A.cols = M->cs->cols.as<int>();
     A.m = (int)mr;
     A.n = (int)M->n;
     A.nwords = nwords;
@@ -964,7 +1053,7 @@ template <class T> void visibility(fluxb200_mesh *M, const int64_t *I, size_t m,
     M->qout.reserve((size_t)total);
     FB_REQUIRE(ceil_div(total, 128) < (1ll << 31), "visibility: too many pairs for one call");
     visibility_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>(
-        M->faceP.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->cols.as<int>(), (int)n,
+        M->faceP.as<Real4<T>>(), M->rows.as<int>(), (int)m, M->cs->cols.as<int>(), (int)n,
         M->face_leaf.as<int>(), M->nodes.as<float4>(), M->tri.as<float4>(), M->ninternal, (int)M->nf,
         M->scalars.as<int>() + 6, brute,
         M->qout.as<uint8_t>());
@@ -1080,11 +1169,12 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
         DevBuf *bufs[] = {&M->V, &M->F, &M->V32, &M->faceP, &M->faceN, &M->keys, &M->vals, &M->left, &M->right,
                           &M->parent, &M->first, &M->last, &M->box, &M->slab, &M->flags, &M->pre, &M->flag_by_pre,
                           &M->top_before, &M->scene, &M->scalars, &M->nodes, &M->tri, &M->face_leaf, &M->node_up, &M->leaf_up, &M->node_range, &M->rows,
-                          &M->cols, &M->ckeys, &M->cvals, &M->colP, &M->colN, &M->col_face, &M->col_leaf,
-                          &M->rank_of_pos, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
+                          &M->ckeys, &M->cvals, &M->lost, &M->bits, &M->row_counts, &M->counts64, &M->indptr, &M->indptr32,
                           &M->tested, &M->out_data, &M->out_indices, &M->qtmp, &M->qout, &M->jbits,
-                          &M->hz, &M->zone_node, &M->zone_up, &M->colH};
+                          &M->hz, &M->zone_node, &M->zone_up};
         for (DevBuf *b : bufs) b->release();
+        for (auto &C : M->colsets) C->release();
+        M->colsets.clear();
         for (int k = 0; k < fluxb200_mesh::kSlots; ++k) {
             M->sbits[k].release(); M->scounts[k].release(); M->scounts64[k].release(); M->sindptr[k].release();
             M->stage_data[k].release(); M->stage_idx[k].release();
@@ -1599,7 +1689,7 @@ int fluxb200_trace_counters(fluxb200_mesh *M, int64_t out[8]) {
         out[4] = (int64_t)h[5];
         out[5] = (int64_t)h[6];
         out[6] = (int64_t)h[7];
-        out[7] = 0;
+        out[7] = M->colset_hits;
     });
 }
 
@@ -1632,6 +1722,11 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
             M->horizon_zone_opt = (int)value;
             M->have_count = false;
             bvh_build(M);
+        } else if (s == "colset_cache") {
+            FB_REQUIRE(value >= 0 && value <= 64, "colset_cache out of range (0..64 prepared column sets)");
+            M->colset_cache_opt = (int)value;
+            for (size_t k = 1; k < M->colsets.size(); ++k) M->colsets[k]->release();
+            M->colsets.resize(std::min<size_t>(M->colsets.size(), 1));
         } else if (s == "trace_variant") {
             FB_REQUIRE(value == 1 || value == 2, "trace_variant must be 1 or 2");
             M->trace_variant_opt = (int)value;

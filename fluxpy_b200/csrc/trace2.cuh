@@ -18,8 +18,9 @@
 //    that is the same for every row of a chunk (bounding box of the target centroids, leaf range,
 //    common ancestor) comes from chunk_info_kernel, once per call.
 //  * the per-lane traversal stack and the per-lane list of candidate triangles live in shared memory
-//    (16 + 6 entries per lane); unit state, the source face and the counters too: the hot loops run
-//    without local memory and without spills at 64 registers.
+//    (8 + 6 entries per lane); unit state, the source face and the counters too: the hot loops run
+//    without local memory and without spills at 64 registers.  The footprint is 39.8 KB per CTA, so that four
+//    CTAs leave 92 KB of the SM's 256 KB to L1 (51.8 KB per CTA with 16-entry stacks measured 1.7 % slower).
 //  * a ray that grazes many triangles (more candidates than its list holds) puts the surplus into a list
 //    shared by the warp; those are Pluecker-tested by ALL lanes at the end of the batch, 32 at a time, the
 //    owner's ray fetched by shuffles (the first generation tested each of them on the spot with one lane
@@ -37,10 +38,22 @@
 
 namespace fluxb200 {
 
-constexpr int kPathCap = 40;   // records of the per-unit list (source path + shared target side)
-constexpr int kStk = 16;       // traversal stack entries per lane (shared memory)
-constexpr int kCand = 6;       // candidate triangles per lane (shared memory)
-constexpr int kOvf = 128;      // ... and per warp for the lanes whose own list is full (grazing rays)
+#ifndef FB_KPATH
+#define FB_KPATH 36
+#endif
+#ifndef FB_KSTK
+#define FB_KSTK 8
+#endif
+#ifndef FB_KCAND
+#define FB_KCAND 6
+#endif
+#ifndef FB_KOVF
+#define FB_KOVF 64
+#endif
+constexpr int kPathCap = FB_KPATH; // records of the per-unit list (source path + shared target side)
+constexpr int kStk = FB_KSTK;      // traversal stack entries per lane (shared memory)
+constexpr int kCand = FB_KCAND;    // candidate triangles per lane (shared memory)
+constexpr int kOvf = FB_KOVF;      // ... and per warp for the lanes whose own list is full (grazing rays)
 constexpr int kFifoCap = 128;  // survivors between the cull and the batches (power of two; < 32 + 2 tiles)
 constexpr int kNodeBits = 26;  // (host check: node ids below 2^26)
 
@@ -355,6 +368,8 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 else break;
             }
         }
+        // (Measured and dropped, profiles/r02d_*: the same loop written for predication -- pushes as selects, one
+        // backward branch -- ran 34.5 ms per slab against 32.5 ms for this form.)
         if (hor) {
             const uint32_t ts = __ballot_sync(0xffffffffu, tskipped);
             if (lane == 0) W->ctr[kCtgt] += (unsigned)__popc(ts);

@@ -373,8 +373,8 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         out = np.zeros(8, np.int64)
         _lib.check(_lib.lib().fluxb200_trace_counters(self._handle, _lib.ptr(out)))
         return dict(rays=int(out[0]), batches=int(out[1]), batches_source_skip=int(out[2]),
-                    rays_target_skip=int(out[3]), rounds=int(out[4]), round_items=int(out[5]),
-                    queue_full_walks=int(out[6]))
+                    rays_target_skip=int(out[3]), rays_resolved_afterwards=int(out[6]),
+                    colset_cache_hits=int(out[7]))
 
     def cuda_stream(self):
         s = ctypes.c_void_p()

@@ -238,14 +238,18 @@ int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
  * "horizon_skip" (1: the trace kernel skips a face's near zone for rays that clear its horizon --
  * exact, see csrc/horizon.cuh; default 1 since it was measured on a B200: trace kernel -30 %), "horizon_zone"
  * (leaves per near zone, default 1023; the target end of the skip needs zones below the 1024-column chunk),
- * "trace_variant" (2: trace kernel with a warp-shared traversal queue, csrc/trace2.cuh, the default;
+ * "colset_cache" (prepared column sets kept per handle, default 8, 0 = none: the sort of J by BVH position and
+ * the gathers are reused by later calls with the same J while P, N, A and the tree are unchanged -- the 16 / 64
+ * root-block calls of CompressedFormFactorMatrix share 4 / 8 column parts),
+ * "trace_variant" (2: second-generation trace kernel, csrc/trace2.cuh, the default;
  * 1: the first-generation kernel with per-lane stacks -- identical results, kept as the A/B reference). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 /* Counters of the last assembly's trace launches: out[0] rays traced (= stats.pairs_tested), and with
  * "horizon_skip" on: out[1] 32-ray batches, out[2] batches walked without the records of the source
  * face's near zone, out[3] rays whose upward walk started at the target's zone node; "trace_variant" 2:
- * out[4] traversal rounds, out[5] items those rounds processed (32 per round = every lane busy),
- * out[6] subtrees / triangles a lane handled itself because a queue was full; out[7] reserved. */
+ * out[4], out[5] unused (counters of a dropped work-queue variant),
+ * out[6] rays handed to the follow-up kernel because a shared-memory stack / list was full; out[7] calls on this
+ * handle (cumulative) that found their column set J already prepared ("colset_cache"). */
 int fluxb200_trace_counters(fluxb200_mesh *mesh, int64_t out[8]);
 
 #ifdef __cplusplus

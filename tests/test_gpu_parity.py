@@ -400,3 +400,41 @@ def test_streaming_and_two_phase_paths_agree(mods):
     for _ in range(3):
         mods['ff'].get_form_factor_matrix(sm, I[:100], J)
     assert np.array_equal(keep.data, snapshot)
+
+
+def test_block_assembly_reuses_prepared_column_sets(mods):
+    """Per-block assembly as CompressedFormFactorMatrix drives it (reference
+    src/flux/compressed_form_factors.py:551-567: every pair of quadrants): the handle keeps the column sets it
+    has prepared, so the 16 calls sort and gather only 4 column parts -- with results identical to a handle
+    that prepares every call, to slices of the full matrix, and to the oracle after the caller changes N in
+    place (which must invalidate every cached set)."""
+    from fluxpy_b200 import blocks
+    V, F = mods['meshes'].gaussian_crater(24, 1, dtype=np.float32)
+    N = mods['meshes'].upward_normals(V, F)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    plain = mods['shape'].CudaTrimeshShapeModel(V, F, N.copy())
+    plain.set_option('colset_cache', 0)
+    parts = blocks.get_quadrant_order(sm.P[:, :2])
+    full = mods['ff'].get_form_factor_matrix(sm)
+    h0 = sm.trace_counters()['colset_cache_hits']
+    B = blocks.assemble_blocks(sm, parts)
+    # 16 calls, 4 distinct column parts: 12 reuses (+ one per call that had to repeat with a larger output buffer)
+    assert 12 <= sm.trace_counters()['colset_cache_hits'] - h0 <= 12 + type(sm).overflow_retries
+    Bp = blocks.assemble_blocks(plain, parts)
+    assert plain.trace_counters()['colset_cache_hits'] == 0
+    for a, I in enumerate(parts):
+        for b, J in enumerate(parts):
+            assert same_csr(B[a][b], Bp[a][b])
+            assert same_csr(B[a][b], full[I, :][:, J].tocsr())
+    # the caller flips normals in place (reference tests/test_form_factors.py:33-34): nothing stale may be used
+    sm.N[::3] *= -1
+    om = mods['oracle'].OracleShapeModel(V, F, N=sm.N.copy())
+    h1, r1 = sm.trace_counters()['colset_cache_hits'], type(sm).overflow_retries
+    assert same_csr(mods['ff'].get_form_factor_matrix(sm, parts[1], parts[2]),
+                    mods['oracle'].get_form_factor_matrix(om, parts[1], parts[2]))
+    assert sm.trace_counters()['colset_cache_hits'] - h1 <= type(sm).overflow_retries - r1   # prepared again
+    # ... and a repeat of that call is served from the cache again, with the same answer
+    h2 = sm.trace_counters()['colset_cache_hits']
+    again = mods['ff'].get_form_factor_matrix(sm, parts[1], parts[2])
+    assert sm.trace_counters()['colset_cache_hits'] >= h2 + 1
+    assert same_csr(again, mods['oracle'].get_form_factor_matrix(om, parts[1], parts[2]))

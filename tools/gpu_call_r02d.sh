@@ -1,0 +1,32 @@
+#!/bin/bash
+# Fourth GPU call of round 2: shared-memory footprint variants of the second-generation trace kernel, the
+# predication-friendly phase C, the SoA emit kernel.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+T=${TAG:-r02d}
+for V in "" _b _c; do
+  FLUXB200_SO=$PWD/fluxpy_b200/libfluxb200$V.so python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sweep --no-full 2>$OUT/${T}_bench$V.err | tail -1 > $OUT/${T}_bench_var$V.json
+done
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sweep --no-full --option trace_variant=1 2>/dev/null | tail -1 > $OUT/${T}_bench_v1.json
+python - <<'PY'
+import glob, json
+for f in sorted(glob.glob('gpurun_out/r02d_bench_*.json')):
+    try:
+        d = json.load(open(f))
+        print(f, 'value %.3e' % d['value'], 'ms/step %.2f' % d['ms_per_step'], 'e2e %.3e' % d['e2e']['value'],
+              'trace ms %.2f' % d['roofline']['launch_ms'], 'frac %.3f' % d['roofline']['frac'], 'lost', d['config']['trace_counters'].get('queue_full_walks'), d.get('parity_check', {}).get('ok'))
+    except Exception as e:
+        print(f, 'unreadable', e)
+PY
+echo "== gpu tier, default"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee $OUT/${T}_tests_default.log
+echo "== launch list of the bench command"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${T}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sweep --no-full > $OUT/${T}_bench_under_ncu.log 2>&1
+echo "== full captures (second repetition): trace, emit"
+ncu --set full --clock-control none --import-source on -k regex:trace2_kernel -s 1 -c 1 -o $OUT/${T}_trace2 \
+    python tools/prof_one.py 4096 317 > $OUT/${T}_prof_one.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:emit_kernel -s 1 -c 1 -o $OUT/${T}_emit \
+    python tools/prof_one.py 4096 317 > /dev/null 2>&1
+ls -la $OUT | tail -12

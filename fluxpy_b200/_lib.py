@@ -198,7 +198,8 @@ class PinnedArena:
         self.free = []
         self.max_free_bytes = max_free_bytes
 
-    def take(self, nbytes):
+    def try_take(self, nbytes):
+        """A free block that fits, or None (no allocation)."""
         nbytes = int(max(nbytes, 1))
         best = None
         for b in self.free:
@@ -206,6 +207,13 @@ class PinnedArena:
                 best = b
         if best is not None and best.nbytes <= 8*nbytes + (1 << 20):
             self.free.remove(best)
+            return best
+        return None
+
+    def take(self, nbytes):
+        nbytes = int(max(nbytes, 1))
+        best = self.try_take(nbytes)
+        if best is not None:
             return best
         p = ctypes.c_void_p()
         want = nbytes + nbytes//8 + 4096          # page-locking is slow: leave room to be reused
@@ -221,6 +229,11 @@ class PinnedArena:
                 lib().fluxb200_host_free(big.ptr)
         except Exception:      # interpreter shutdown
             pass
+
+    def release_free(self):
+        """Unlock and free every block that is not in use."""
+        while self.free:
+            lib().fluxb200_host_free(self.free.pop().ptr)
 
     def discard(self, block):
         """Return a block that was never leased."""

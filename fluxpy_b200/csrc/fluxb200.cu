@@ -103,6 +103,7 @@ struct fluxb200_mesh {
     // host threads write the indices (host_expand.cpp)
     static constexpr int kHostSlots = 8; // ring of page-locked word buffers (sub-slabs in flight on the host)
     HostBuf h_jbits;
+    HostBuf h_data[kHostSlots]; // destination 3 (pageable output): page-locked staging of a sub-slab's values
     HostExpander expander;
     int host_expand_opt = 1;
     int host_threads_opt = 0; // 0 = automatic
@@ -750,7 +751,13 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
                                     double eps, int index_width, int destination, void *indptr,
                                     void *indices, void *data, int64_t capacity, int64_t *row_counts) {
     FB_REQUIRE(index_width == 4 || index_width == 8, "index_width must be 4 or 8");
-    FB_REQUIRE(destination == 0 || destination == 2, "destination must be 0 (host) or 2 (library device buffers)");
+    FB_REQUIRE(destination == 0 || destination == 2 || destination == 3,
+               "destination must be 0 (page-locked host buffers), 2 (library device buffers) or 3 (ordinary host buffers)");
+    // 3 = host output into ORDINARY (pageable) memory: page-locking a multi-gigabyte result costs more than
+    // assembling it (about 0.5 s per GB), so the values go through page-locked staging slots and host threads
+    // move them on; the column indices are written by host threads anyway.  Otherwise identical to 0.
+    const bool staged = destination == 3;
+    if (staged) destination = 0;
     if (index_width == 4) FB_REQUIRE(n < (1ull << 31), "int32 indices cannot hold this many columns");
     cudaStream_t s0 = M->stream, s1 = M->copy_stream, s2 = M->d2h_stream;
     FB_CUDA(cudaEventRecord(M->ev[0], s0));
@@ -786,7 +793,7 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     }
     // host output: the column indices travel as J-order visibility words (n/8 bytes per row instead
     // of 4 or 8 bytes per entry) and host threads expand them while the next sub-slabs are traced
-    const bool expand = destination == 0 && M->host_expand_opt != 0 && n > 0;
+    const bool expand = destination == 0 && (M->host_expand_opt != 0 || staged) && n > 0;
     const size_t slot_words = sub * (size_t)std::max(M->nwords, 1);
     std::vector<std::unique_ptr<ExpandTask>> tasks(expand ? nsub : 0);
     struct TaskGuard { // no worker may outlive the buffers it writes to, whatever path leaves this frame
@@ -906,8 +913,16 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
             if (destination == 0) {
                 FB_CUDA(cudaStreamWaitEvent(s2, M->slot_free[b], 0));
                 if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k + 2], s2));
-                FB_CUDA(cudaMemcpyAsync((char *)data + sizeof(T) * (size_t)off, d_data, sizeof(T) * (size_t)nnz_k,
-                                        cudaMemcpyDeviceToHost, s2));
+                char *h_stage = nullptr;
+                if (staged) { // (the slot is free: its last user, sub-slab k - kHostSlots, is waited for just below)
+                    if (k >= (size_t)fluxb200_mesh::kHostSlots && tasks[k - fluxb200_mesh::kHostSlots])
+                        M->expander.wait(tasks[k - fluxb200_mesh::kHostSlots].get());
+                    HostBuf &hb = M->h_data[k % fluxb200_mesh::kHostSlots];
+                    hb.reserve(sizeof(T) * (size_t)nnz_k);
+                    h_stage = hb.as<char>();
+                }
+                FB_CUDA(cudaMemcpyAsync(staged ? (void *)h_stage : (void *)((char *)data + sizeof(T) * (size_t)off), d_data,
+                                        sizeof(T) * (size_t)nnz_k, cudaMemcpyDeviceToHost, s2));
                 d2h_bytes += (int64_t)(sizeof(T) * (size_t)nnz_k);
                 d2h_bytes += expand ? (int64_t)(sizeof(uint32_t) * mr * (size_t)M->nwords)
                                     : (int64_t)((size_t)index_width * (size_t)nnz_k);
@@ -928,6 +943,11 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
                     for (size_t r = 0; r < mr; ++r) t->offs[r + 1] = t->offs[r] + (int64_t)h_counts[row0 + r];
                     t->indices = indices;
                     t->index_width = index_width;
+                    if (staged) {
+                        t->copy_src = h_stage;
+                        t->copy_dst = (char *)data + sizeof(T) * (size_t)off;
+                        t->copy_bytes = sizeof(T) * (size_t)nnz_k;
+                    }
                     t->pieces = (int)std::max<size_t>(1, std::min<size_t>(mr, 2 * (size_t)M->expander.threads()));
                     t->pending.store(t->pieces);
                     t->owner = &M->expander;
@@ -1183,6 +1203,7 @@ int fluxb200_mesh_destroy(fluxb200_mesh *M) {
             if (M->d2h_done[k]) cudaEventDestroy(M->d2h_done[k]);
         }
         M->h_nnz.release(); M->h_counts.release(); M->h_jbits.release();
+        for (auto &hb : M->h_data) hb.release();
         for (auto &e : M->sub_events) cudaEventDestroy(e);
         for (auto &e : M->tl_events) cudaEventDestroy(e);
         if (M->copy_stream) { cudaStreamSynchronize(M->copy_stream); cudaStreamDestroy(M->copy_stream); }

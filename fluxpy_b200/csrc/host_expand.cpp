@@ -223,6 +223,12 @@ void HostExpander::run() {
             char *dst = reinterpret_cast<char *>(t->indices) + (size_t)t->index_width * (size_t)t->offs[r];
             expand_words(w, t->nwords, t->index_width, dst, bits);
         }
+        if (t->copy_bytes) {
+            const size_t b0 = t->copy_bytes * (size_t)item.second / (size_t)t->pieces & ~(size_t)63;
+            const size_t b1 = item.second + 1 == t->pieces ? t->copy_bytes
+                                                           : (t->copy_bytes * (size_t)(item.second + 1) / (size_t)t->pieces & ~(size_t)63);
+            if (b1 > b0) memcpy(t->copy_dst + b0, t->copy_src + b0, b1 - b0);
+        }
         if (t->pending.fetch_sub(1) == 1) {
             std::lock_guard<std::mutex> lk(mu_); // pairs with the predicate check in wait()
             cv_done_.notify_all();

@@ -26,6 +26,11 @@ struct ExpandTask {
     std::vector<int64_t> offs; // mr + 1 positions in `indices`
     void *indices = nullptr;
     int index_width = 4;
+    // optional second job of the same sub-slab: values that were copied out into a page-locked staging
+    // slot go on to the caller's ordinary (pageable) array; every piece copies its share of the bytes
+    const char *copy_src = nullptr;
+    char *copy_dst = nullptr;
+    size_t copy_bytes = 0;
     int pieces = 1;               // row ranges handed to the workers
     std::atomic<int> pending{0};  // pieces not finished yet
     std::atomic<int> queued{0};   // set once the stream callback has submitted it

@@ -274,13 +274,27 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
-    #: nnz / (m*n) of this shape model's recent calls (the larger of the last one and 0.9 x the estimate before
-    #: it): sizes the streaming output buffers, with 20 % headroom, so that a retry is the exception.  Per
-    #: instance, and it decays: one dense block must not make every later call page-lock m*n entries.
+    #: nnz / (m*n): sizes the streaming output buffers, with 20 % headroom, so that a retry is the exception.
+    #: Kept per shape model AND per call shape (m, n) -- the largest seen for that shape, so that repeated
+    #: calls of one shape settle on one recycled page-locked block (a decaying estimate made a 20-step loop
+    #: re-lock 3.4 GB in its ninth step: 2.2 s) -- while a dense small block cannot inflate the buffers of
+    #: large calls; a shape seen for the first time starts from the most recent ratio of the model.
     _fill_ratio = 0.55
     overflow_retries = 0
+    pageable_results = 0
+    #: host results above this size go to ordinary (pageable) memory unless a recycled page-locked block fits
+    pageable_above_bytes = 4 << 30   # (a 4096 x 200k slab is 3.4 GB: recycled page-locked blocks serve repeated calls best)
     #: results below this many bytes are copied to ordinary memory and their page-locked block goes back to the arena
     small_result_bytes = 1 << 20
+
+    def _note_fill_ratio(self, m, n, nnz):
+        if m*n:
+            r = max(0.02, nnz/(m*n))
+            ratios = self.__dict__.setdefault('_fill_ratio_by_shape', {})
+            if len(ratios) > 4096:
+                ratios.clear()
+            ratios[(m, n)] = max(r, ratios.get((m, n), 0.0))
+            self._fill_ratio = r
 
     def _ff_assemble_host(self, I, J, eps, want_row_counts=False, index_dtype=None):
         """Streaming assembly (``fluxb200_ff_assemble``) into page-locked host
@@ -295,18 +309,40 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         counts = np.empty(m, np.int64) if want_row_counts else None
         st = _lib.FFStats()
         esz = np.dtype(self.dtype).itemsize
-        cap = int(min(m*n, max(1024, self._fill_ratio*1.2*m*n + 4096)))
+        ratios = self.__dict__.setdefault('_fill_ratio_by_shape', {})
+        ratio = ratios.get((m, n), self._fill_ratio)
+        cap = int(min(m*n, max(1024, ratio*1.2*m*n + 4096)))
         while True:
             idt = index_dtype or (np.int32 if max(cap, n, m + 1) < 2**31 else np.int64)
             isz = np.dtype(idt).itemsize
             off_idx = -(-(cap*esz)//256)*256
             off_ptr = off_idx + -(-(cap*isz)//256)*256
-            block = _lib.arena.take(off_ptr + (m + 1)*isz)
-            rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), isz, 0,
-                                        block.ptr + off_ptr, block.ptr + off_idx, block.ptr, cap,
+            need = off_ptr + (m + 1)*isz
+            block = _lib.arena.try_take(need)
+            pageable = None
+            if block is None and need > self.pageable_above_bytes:
+                # no recycled page-locked block fits and this one would cost about 0.5 s per GB to lock:
+                # ordinary memory, the library stages the copy-out (C ABI destination 3)
+                pageable = np.empty(need, np.uint8)
+                base, dest = pageable.ctypes.data, 3
+                type(self).pageable_results += 1
+            else:
+                block = block or _lib.arena.take(need)
+                base, dest = block.ptr, 0
+            rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), isz, dest,
+                                        base + off_ptr, base + off_idx, base, cap,
                                         _lib.ptr(counts), ctypes.byref(st))
+            if pageable is not None and rc != _lib.OVERFLOW:
+                _lib.check(rc)
+                nnz = int(st.nnz)
+                self._note_fill_ratio(m, n, nnz)
+                data = pageable[:nnz*esz].view(self.dtype)
+                indices = pageable[off_idx:off_idx + nnz*isz].view(idt)
+                indptr = pageable[off_ptr:off_ptr + (m + 1)*isz].view(idt)
+                return m, n, indptr, indices, data, counts, st
             if rc == _lib.OVERFLOW:      # too many entries for the buffer, or for int32 offsets: st.nnz = the count
-                _lib.arena.discard(block)
+                if block is not None:
+                    _lib.arena.discard(block)
                 type(self).overflow_retries += 1
                 cap = int(st.nnz)
                 if index_dtype is not None and np.dtype(index_dtype).itemsize == 4 and cap >= 2**31:
@@ -317,8 +353,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                 _lib.check(rc)
             break
         nnz = int(st.nnz)
-        if m*n:
-            self._fill_ratio = max(0.02, nnz/(m*n), 0.9*self._fill_ratio)
+        self._note_fill_ratio(m, n, nnz)
         data, indices, indptr = _lib.arena.arrays(
             block, [(0, nnz, self.dtype), (off_idx, nnz, idt), (off_ptr, m + 1, idt)])
         if nnz*(esz + isz) + (m + 1)*isz <= self.small_result_bytes:

@@ -132,6 +132,10 @@ int fluxb200_ff_fill(fluxb200_mesh *mesh, int index_width, int destination, void
  *                (nothing usable was written; call again with more room).
  * destination 2: library-owned device buffers (grown as needed; capacity <= 0
  *                uses the previous size as the first guess).
+ * destination 3: as 0, for ORDINARY (pageable) host buffers: the values pass through page-locked staging slots
+ *                inside the library and host threads move them on (the column indices are written by host
+ *                threads in either case).  Page-locking a multi-gigabyte result costs several times what
+ *                assembling it does (about 0.5 s per GB measured); this mode pays a memcpy instead.
  * row_counts: optional int64[m] (host). */
 int fluxb200_ff_assemble(fluxb200_mesh *mesh, const int64_t *I, size_t m, const int64_t *J, size_t n,
                          double eps, int index_width, int destination, void *indptr, void *indices,

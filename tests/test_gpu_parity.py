@@ -372,9 +372,18 @@ def test_streaming_and_two_phase_paths_agree(mods):
     ref = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n))
     for sub in (7, 64, 512, 4096):
         sm.set_option('sub_rows', sub)
-        type(sm)._fill_ratio = 0.05            # force the overflow + retry path
+        sm._fill_ratio = 0.05                  # force the overflow + retry path
+        sm.__dict__.pop('_fill_ratio_by_shape', None)
+        r0 = type(sm).overflow_retries
         FF = mods['ff'].get_form_factor_matrix(sm, I, J)
-        assert same_csr(FF, ref)
+        assert same_csr(FF, ref) and type(sm).overflow_retries == r0 + 1
+        # ordinary (pageable) output arrays: values staged through page-locked slots, moved on by host threads
+        _lib.arena.release_free()              # (a recycled page-locked block that fits would be preferred)
+        sm.pageable_above_bytes, p0 = 0, type(sm).pageable_results
+        _, _, ipp, ixp, dvp, _, _ = sm._ff_assemble_host(I, J, 1e-5)
+        assert type(sm).pageable_results == p0 + 1
+        assert np.array_equal(ipp, ip) and np.array_equal(ixp, ix) and np.array_equal(dvp, dv)
+        sm.pageable_above_bytes = type(sm).pageable_above_bytes
         m2, n2, ip2, ix2, dv2, c2, st2 = sm._ff_assemble_host(I, J, 1e-5, want_row_counts=True)
         assert np.array_equal(c2, counts) and st2.nnz == st.nnz and st2.pairs_tested == st.pairs_tested
         # copy-out: column indices expanded on the host from the visibility words (default) ==

@@ -285,7 +285,7 @@ def sweep_arm(ctx, grid, dtype, rows_want, steps=3, warmup=2):
     nf = F.shape[0]
     rows = min(rows_want, nf)
     stream = torch.cuda.ExternalStream(sm.cuda_stream(), device=dev)
-    acc = {'tested': 0, 'pairs': 0, 'trace_ms': 0.0, 'launches': 0, 'trace_launches': 0}
+    acc = {'tested': 0, 'pairs': 0, 'trace_ms': 0.0, 'fill_ms': 0.0, 'prepare_ms': 0.0, 'launches': 0, 'trace_launches': 0}
 
     def step(s, timed):
         I = slab_rows(s, rank, world, rows, nf)
@@ -296,6 +296,8 @@ def sweep_arm(ctx, grid, dtype, rows_want, steps=3, warmup=2):
             acc['tested'] += st.pairs_tested
             acc['pairs'] += st.pairs_all
             acc['trace_ms'] += st.ms_trace
+            acc['fill_ms'] += st.ms_fill
+            acc['prepare_ms'] += st.ms_prepare
             acc['trace_launches'] += st.trace_launches
             acc['launches'] += st.kernel_launches + 1
 
@@ -317,7 +319,8 @@ def sweep_arm(ctx, grid, dtype, rows_want, steps=3, warmup=2):
     del sm
     return {'faces': int(nf), 'grid': grid, 'dtype': 'f64' if dtype == np.float64 else 'f32', 'rows_per_step_per_gpu': rows,
             'steps': steps, 'pairs_per_s': tested/(ms/1e3), 'pairs_all_per_s': pairs/(ms/1e3), 'ms_per_step': ms/steps,
-            'trace_ms_per_launch': 1e3*trace_s, 'roofline_frac': fl/trace_s/1e12/peak,
+            'trace_ms_per_launch': 1e3*trace_s, 'fill_ms_per_step': acc['fill_ms']/steps,
+            'prepare_ms_per_step': acc['prepare_ms']/steps, 'roofline_frac': fl/trace_s/1e12/peak,
             'roofline_peak_tflops': peak}
 
 

@@ -50,6 +50,9 @@ namespace fluxb200 {
 #ifndef FB_KOVF
 #define FB_KOVF 64
 #endif
+#ifndef FB_C_FORM
+#define FB_C_FORM 0 // loop form of phase C (tuning variants)
+#endif
 constexpr int kPathCap = FB_KPATH; // records of the per-unit list (source path + shared target side)
 constexpr int kStk = FB_KSTK;      // traversal stack entries per lane (shared memory)
 constexpr int kCand = FB_KCAND;    // candidate triangles per lane (shared memory)
@@ -350,6 +353,29 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
             }
         }
         // ---- phase C: the subtrees that were actually hit, top-down, every lane on its own -------------
+#if FB_C_FORM == 1
+        { // the loop form of the first-generation kernel: one flag, one select, pop or stop when nothing was hit
+            int node = 0;
+            bool walking = active && sp > 0;
+            if (walking) node = lds_i1(stk + (uint32_t)(--sp) * 128u);
+            while (walking) {
+                float4 q[6];
+                load_node<false>(bvh, node, q);
+                const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
+                const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
+                const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                if (h0 && r0 < 0 && ~r0 != tleaf) push(r0);
+                if (h1 && r1 < 0 && ~r1 != tleaf) push(r1);
+                const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
+                if (i0 && i1) push(r1);
+                node = i0 ? r0 : r1;
+                if (!(i0 || i1)) {
+                    if (sp > 0) node = lds_i1(stk + (uint32_t)(--sp) * 128u);
+                    else walking = false;
+                }
+            }
+        }
+#else
         if (active && sp > 0) {
             int node = lds_i1(stk + (uint32_t)(--sp) * 128u);
             while (true) {
@@ -368,6 +394,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 else break;
             }
         }
+#endif
         // (Measured and dropped, profiles/r02d_*: the same loop written for predication -- pushes as selects, one
         // backward branch -- ran 34.5 ms per slab against 32.5 ms for this form.)
         if (hor) {

@@ -142,6 +142,22 @@ def _index_array(I):
     return np.ascontiguousarray(np.asarray(I).astype(np.int64))
 
 
+def _pageable_buffer(nbytes):
+    """``nbytes`` of ordinary host memory as a uint8 array; transparent huge pages are requested where the
+    kernel offers them (2 MB pages: 512 times fewer first-touch page faults when the library's host threads
+    fill a multi-gigabyte result)."""
+    try:
+        import mmap
+        buf = mmap.mmap(-1, int(nbytes), flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
+        try:
+            buf.madvise(mmap.MADV_HUGEPAGE)
+        except (AttributeError, OSError, ValueError):
+            pass
+        return np.frombuffer(buf, dtype=np.uint8)
+    except (ImportError, OSError, ValueError):
+        return np.empty(int(nbytes), np.uint8)
+
+
 class CudaTrimeshShapeModel(TrimeshShapeModel):
     """B200 backend: the four hooks of shape.py:261-292 / 295-421 plus the fused
     assembly hook, all through the C ABI of ``libfluxb200.so``."""
@@ -282,8 +298,9 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
     _fill_ratio = 0.55
     overflow_retries = 0
     pageable_results = 0
-    #: host results above this size go to ordinary (pageable) memory unless a recycled page-locked block fits
-    pageable_above_bytes = 4 << 30   # (a 4096 x 200k slab is 3.4 GB: recycled page-locked blocks serve repeated calls best)
+    #: host results above this size, of a call shape not seen before, go to ordinary (pageable) memory unless a
+    #: recycled page-locked block fits
+    pageable_above_bytes = 4 << 30
     #: results below this many bytes are copied to ordinary memory and their page-locked block goes back to the arena
     small_result_bytes = 1 << 20
 
@@ -320,10 +337,13 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
             need = off_ptr + (m + 1)*isz
             block = _lib.arena.try_take(need)
             pageable = None
-            if block is None and need > self.pageable_above_bytes:
-                # no recycled page-locked block fits and this one would cost about 0.5 s per GB to lock:
-                # ordinary memory, the library stages the copy-out (C ABI destination 3)
-                pageable = np.empty(need, np.uint8)
+            if block is None and need > self.pageable_above_bytes and (m, n) not in ratios:
+                # A large result of a call shape seen for the first time, and no recycled page-locked block
+                # fits: locking one would cost about 0.25 s per GB, so it goes to ordinary memory and the
+                # library stages the copy-out (C ABI destination 3: page faults + a memcpy, 0.2-0.3 s per GB,
+                # no locked memory left behind).  Repeated shapes (row slabs in a loop, block assembly) always
+                # get page-locked blocks: locked once, recycled by the arena, copied into at PCIe speed.
+                pageable = _pageable_buffer(need)
                 base, dest = pageable.ctypes.data, 3
                 type(self).pageable_results += 1
             else:

@@ -589,7 +589,7 @@ def main():
         step_e2e(s)
     barrier()
     t0 = time.perf_counter()
-    e2e = {'tested': 0, 'h2d': 0, 'd2h': 0, 'step_ms': []}
+    e2e = {'tested': 0, 'h2d': 0, 'd2h': 0, 'idx_bytes': 0, 'step_ms': []}
     for s in range(args.warmup, args.warmup + args.steps):
         ts = time.perf_counter()
         st, h2d, d2h, _ = step_e2e(s)
@@ -597,6 +597,7 @@ def main():
         e2e['tested'] += st['pairs_tested']
         e2e['h2d'] += h2d
         e2e['d2h'] += d2h
+        e2e['idx_bytes'] += 4*st['nnz']                 # int32 column indices written by the host threads
     barrier()
     t_e2e = time.perf_counter() - t0
 
@@ -626,6 +627,7 @@ def main():
     d2h_gbs = pcie_probe(ctx)
     d2h_gbs_min = -allmax(-d2h_gbs)
     d2h_gbs_sum = allsum(d2h_gbs)
+    host_bytes_all = allsum(e2e['d2h'] + e2e['idx_bytes'])   # everything the step writes into host DRAM, all ranks
     # ---- after the timed regions: N-GPU result == one-GPU result, on the box the driver runs --------------
     s_last = args.warmup + args.steps - 1
     parity = parity_check(ctx, lambda r: slab_rows(s_last, r, world, args.rows, nf), last_slab or None)
@@ -712,6 +714,12 @@ def main():
                     'd2h_probe_gbs_slowest_rank': d2h_gbs_min, 'd2h_probe_gbs_all_ranks': d2h_gbs_sum,
                     'pcie_floor_ms': e2e['d2h']/steps/(d2h_gbs_min*1e9)*1e3,
                     'ms_per_step_over_floor': (1e3*t_e2e_max/steps)/(e2e['d2h']/steps/(d2h_gbs_min*1e9)*1e3),
+                    # the box's host side moves a fixed total (the probe's sum over ranks) whoever writes: the DMA of
+                    # values + visibility words AND the host threads' index stores share it
+                    'host_write_bytes_per_step_all_ranks': host_bytes_all/steps,
+                    'host_memory_floor_ms': host_bytes_all/steps/(d2h_gbs_sum*1e9)*1e3,
+                    'ms_per_step_over_host_memory_floor': (1e3*t_e2e_max/steps)/(host_bytes_all/steps/(d2h_gbs_sum*1e9)*1e3),
+                    'step_ms_median_rank0': float(np.median(e2e['step_ms'])),
                     'bound': 'host side of the copy-out (PCIe DMA + index expansion both write host DRAM)'
                              if (1e3*t_e2e_max/steps) > 1.5*ms_dev_max/steps else 'trace kernel (copy-out hidden under it)',
                     'output_buffer_retries': fluxpy_b200.CudaTrimeshShapeModel.overflow_retries},

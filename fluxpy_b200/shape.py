@@ -290,7 +290,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         _lib.check(_lib.lib().fluxb200_ff_fill(self._handle, index_width, 2, None, None, None, ctypes.byref(st)))
         return st
 
-    #: nnz / (m*n): sizes the streaming output buffers, with 30 % headroom, so that a retry is the exception.
+    #: nnz / (m*n): sizes the streaming output buffers, with 50 % headroom, so that a retry is the exception.
     #: Kept per shape model AND per call shape (m, n) -- the largest seen for that shape, so that repeated
     #: calls of one shape settle on one recycled page-locked block (a decaying estimate made a 20-step loop
     #: re-lock 3.4 GB in its ninth step: 2.2 s) -- while a dense small block cannot inflate the buffers of
@@ -328,9 +328,10 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         esz = np.dtype(self.dtype).itemsize
         ratios = self.__dict__.setdefault('_fill_ratio_by_shape', {})
         ratio = ratios.get((m, n), self._fill_ratio)
-        # 30 % headroom (+ 12.5 % in the arena's block): the row slabs of one mesh differ by +-15 % in their entry
-        # counts, a short buffer costs a re-trace AND a new page-locked block (1.9 s inside a timed loop, r02g)
-        cap = int(min(m*n, max(1024, ratio*1.3*m*n + 4096)))
+        # 50 % headroom (+ 12.5 % in the arena's block): the row slabs of one mesh differ by up to 1.4x in their
+        # entry counts (crater floor against rim), and a short buffer costs a re-trace AND a new page-locked block
+        # -- 1.9 s inside a timed loop on 2 GPUs, 3.2 s on 8 with every rank locking at once (r02g, r02h)
+        cap = int(min(m*n, max(1024, ratio*1.5*m*n + 4096)))
         while True:
             idt = index_dtype or (np.int32 if max(cap, n, m + 1) < 2**31 else np.int64)
             isz = np.dtype(idt).itemsize
@@ -366,7 +367,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                 if block is not None:
                     _lib.arena.discard(block)
                 type(self).overflow_retries += 1
-                cap = int(st.nnz)
+                cap = int(min(m*n, st.nnz + st.nnz//4))      # (room for the next, denser slab of this shape)
                 if index_dtype is not None and np.dtype(index_dtype).itemsize == 4 and cap >= 2**31:
                     raise RuntimeError('int32 indices cannot hold this matrix')
                 continue

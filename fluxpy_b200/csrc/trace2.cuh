@@ -209,6 +209,30 @@ template <> __device__ __forceinline__ Real4<double> get_real4<double>(const dou
     return Real4<double>{a.x, a.y, b.x, b.y};
 }
 
+// make_raybox (trace.cuh) with the hardware's approximate reciprocal (1 ulp) instead of three IEEE divisions
+// (~30 instructions per batch): the box test only has to be conservative, and its final comparison carries a
+// guard band of 2e-6 relative -- twenty times the error introduced here.
+__device__ __forceinline__ RayBox make_raybox_fast(const Ray &r) {
+    auto inv = [](float d) {
+        const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+        float q;
+#ifndef FB_EMU
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(a));
+#else
+        q = 1.0f / a;
+#endif
+        return q;
+    };
+    RayBox rb;
+    rb.ix = inv(r.dx);
+    rb.iy = inv(r.dy);
+    rb.iz = inv(r.dz);
+    rb.ox = r.ox * rb.ix;
+    rb.oy = r.oy * rb.iy;
+    rb.oz = r.oz * rb.iz;
+    return rb;
+}
+
 #ifdef FB_EMU
 #define FB_COUNT2(k, v) FB_COUNT(k, v)
 #define FB_CHECK(cond) do { if (!(cond)) { fprintf(stderr, "trace2 check failed line %d: %s\n", __LINE__, #cond); abort(); } } while (0)
@@ -262,11 +286,12 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
         }
         if (lane == 0) W->novf = 0u, W->ovfhit = 0u;
         __syncwarp();
-        const RayBox rb = make_raybox(ray);
+        const RayBox rb = make_raybox_fast(ray);
         const float tmax = tj * 1.000002f;
         // per-lane stack of hit nodes and list of candidate triangles, both in shared memory: [entry][lane]
         smem_addr_t stk = (smem_addr_t)__cvta_generic_to_shared(&W->stack[0][lane]);
         smem_addr_t cnd = (smem_addr_t)__cvta_generic_to_shared(&W->cand[0][lane]);
+        asm volatile("" : "+r"(stk), "+r"(cnd)); // keep them: do not rebuild the addresses at every push
         int sp = 0, nl = 0;
         bool lost = false; // something did not fit: the column is traced again, on its own, at the end of the unit
         auto push = [&](int ref) {

@@ -378,7 +378,8 @@ def test_streaming_and_two_phase_paths_agree(mods):
         FF = mods['ff'].get_form_factor_matrix(sm, I, J)
         assert same_csr(FF, ref) and type(sm).overflow_retries == r0 + 1
         # ordinary (pageable) output arrays: values staged through page-locked slots, moved on by host threads
-        _lib.arena.release_free()              # (a recycled page-locked block that fits would be preferred)
+        _lib.arena.release_free()              # (a recycled page-locked block that fits would be preferred,
+        sm.__dict__.pop('_fill_ratio_by_shape', None)   # and so would a new one for a call shape seen before)
         sm.pageable_above_bytes, p0 = 0, type(sm).pageable_results
         _, _, ipp, ixp, dvp, _, _ = sm._ff_assemble_host(I, J, 1e-5)
         assert type(sm).pageable_results == p0 + 1

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 const float4 *rec = A.nodes + 6 * (size_t)p + 3 * (1 - slot);
                 if (lane < 3) path_s[warp][3 * npath + lane] = __ldg(rec + lane);
                 if (lane == 3) {
-                    const int ref = __float_as_int(__ldg(rec).w);
+                    const int ref = rec_ref(__ldg(rec + 2));
                     range_s[warp][npath] = ref < 0 ? make_int2(~ref, ~ref) : A.node_range[ref];
                 }
                 ++npath;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
             for (int e = 0; e < npath; ++e)
                 if (range_s[warp][e].x <= leaf_lo && leaf_hi <= range_s[warp][e].y) xe = e;
             if (xe >= 0 && leaf_lo != leaf_hi) {
-                const int xr = __float_as_int(path_s[warp][3 * xe].w);
+                const int xr = rec_ref(path_s[warp][3 * xe + 2]);
                 int c = A.leaf_up[leaf_lo] >> 1;
                 while (!(A.node_range[c].x <= leaf_lo && leaf_hi <= A.node_range[c].y)) c = A.node_up[c] >> 1;
                 int cur = c, n2 = npath;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     const float4 *rec = A.nodes + 6 * (size_t)pp + 3 * (1 - slot);
                     if (lane < 3) path_s[warp][3 * n2 + lane] = __ldg(rec + lane);
                     if (lane == 3) {
-                        const int ref = __float_as_int(__ldg(rec).w);
+                        const int ref = rec_ref(__ldg(rec + 2));
                         range_s[warp][n2] = ref < 0 ? make_int2(~ref, ~ref) : A.node_range[ref];
                     }
                     ++n2;
@@ -344,13 +344,14 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     ra[h] = a; rb2[h] = b; rc[h] = cc; rr[h] = rg;
                     bool keep = true;
                     if (A.shaft_filter && (rg.y < leaf_lo || rg.x > leaf_hi)) { // holds no target of this chunk
-                        if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keep = false;
+                        // record layout: a = (lo.x, hi.x, lo.y, hi.y), b = (lo.z, hi.z, slab_min, slab_max), cc = (dir | ref)
+                        if (a.x > h0h || a.y < h0l || a.z > h1h || a.w < h1l || b.x > h2h || b.y < h2l) keep = false;
                         // extent of the hull along the slab direction
                         const float sp = cc.x * px + cc.y * py + cc.z * pz;
                         const float lo_s = fminf(cc.x * bl0, cc.x * bh0) + fminf(cc.y * bl1, cc.y * bh1) + fminf(cc.z * bl2, cc.z * bh2);
                         const float hi_s = fmaxf(cc.x * bl0, cc.x * bh0) + fmaxf(cc.y * bl1, cc.y * bh1) + fmaxf(cc.z * bl2, cc.z * bh2);
                         const float spad = pad * (fabsf(cc.x) + fabsf(cc.y) + fabsf(cc.z));
-                        if (fminf(sp, lo_s) - spad > cc.w || fmaxf(sp, hi_s) + spad < b.w) keep = false;
+                        if (fminf(sp, lo_s) - spad > b.w || fmaxf(sp, hi_s) + spad < b.z) keep = false;
                     }
                     if (e != xdrop) {
                         keepr[h] = keep;
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     for (int ks = 0; ks < nuse; ++ks, addr += 48) {
                         const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
                         if (child_hit(ray, rb, a, b, cc, tmax_a)) {
-                            const int ref = __float_as_int(a.w);
+                            const int ref = rec_ref(cc);
                             if (ref < 0) push_leaf(~ref);
                             else push_node(ref);
                         }
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     for (int ks = 0; ks < nuse; ++ks, addr += 48, raddr += 8) {
                         const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
                         const int2 rg = lds_i2(raddr);
-                        const int ref = __float_as_int(a.w);
+                        const int ref = rec_ref(cc);
                         if (tleaf >= rg.x && tleaf <= rg.y) {
                             xref = ref;
                             if constexpr (kHor) xbig = rg.y - rg.x + 1 > A.zone_leaves;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                     ++emu_nb;
 #endif
                     if (child_hit(ray, rb, a, b, cc, tmax)) {
-                        const int ref = __float_as_int(a.w);
+                        const int ref = rec_ref(cc);
                         if (ref < 0) push_leaf(~ref);
                         else push_node(ref);
                     }
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace_kern
                 load_node<kTop>(bvh, node, q);
                 const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
                 const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
-                const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                const int r0 = rec_ref(q[2]), r1 = rec_ref(q[5]);
                 if (h0 && r0 < 0 && ~r0 != tleaf) push_leaf(~r0);
                 if (h1 && r1 < 0 && ~r1 != tleaf) push_leaf(~r1);
                 const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;

@@ -1269,6 +1269,16 @@ int fluxb200_bvh_export(fluxb200_mesh *M, float *nodes, int32_t *leaf_face) {
             FB_CUDA(cudaMemcpyAsync(leaf_face, M->vals.p, sizeof(int32_t) * M->nf, cudaMemcpyDeviceToHost,
                                     M->stream));
         FB_CUDA(cudaStreamSynchronize(M->stream));
+        if (nodes) { // the documented export layout per child: (lo.xyz, ref) (hi.xyz, slab_min) (slab_dir.xyz, slab_max);
+            // on the device the records are stored pair-aligned for the packed box / slab test (trace.cuh child_hit)
+            for (size_t k = 0; k < 2 * (size_t)M->ninternal; ++k) {
+                float *q = nodes + 12 * k;
+                const float d[12] = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8], q[9], q[10], q[11]};
+                q[0] = d[0]; q[1] = d[2]; q[2] = d[4]; q[3] = d[11];   // lo.xyz | ref
+                q[4] = d[1]; q[5] = d[3]; q[6] = d[5]; q[7] = d[6];    // hi.xyz | slab_min
+                q[8] = d[8]; q[9] = d[9]; q[10] = d[10]; q[11] = d[7]; // slab_dir | slab_max
+            }
+        }
     });
 }
 

@@ -349,7 +349,7 @@ __global__ void preorder_kernel(int n, const int *__restrict__ left, const int *
 }
 
 // 96-byte internal node = two children, each three float4:
-//   (lo.xyz, bits(ref))  (hi.xyz, slab_min)  (slab_dir.xyz, slab_max)
+//   (lo.x, hi.x, lo.y, hi.y)  (lo.z, hi.z, slab_min, slab_max)  (slab_dir.xyz, bits(ref))
 // ref >= 0: internal node index, ref < 0: triangle ~ref (leaf order).
 // Order: the ntop internal nodes with the largest subtrees first (pre-order
 // among themselves; the prefix staged in shared memory), then the rest in
@@ -389,9 +389,10 @@ __global__ void flatten_kernel(int n, const int *__restrict__ left, const int *_
             smin = ord_flt(umin) - pad;
             smax = ord_flt(umax) + pad;
         }
-        nodes[6 * (size_t)me + 3 * c + 0] = make_float4(b[0], b[1], b[2], __int_as_float(ref));
-        nodes[6 * (size_t)me + 3 * c + 1] = make_float4(b[3], b[4], b[5], smin);
-        nodes[6 * (size_t)me + 3 * c + 2] = make_float4(b[6], b[7], b[8], smax);
+        // (lo.x, hi.x, lo.y, hi.y) (lo.z, hi.z, slab_min, slab_max) (slab_dir.xyz | ref): see trace.cuh child_hit
+        nodes[6 * (size_t)me + 3 * c + 0] = make_float4(b[0], b[3], b[1], b[4]);
+        nodes[6 * (size_t)me + 3 * c + 1] = make_float4(b[2], b[5], smin, smax);
+        nodes[6 * (size_t)me + 3 * c + 2] = make_float4(b[6], b[7], b[8], __int_as_float(ref));
     }
 }
 

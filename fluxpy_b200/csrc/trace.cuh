@@ -125,10 +125,48 @@ struct BvhView {
     int *error_flag;      // set to 1 on traversal stack overflow
 };
 
+// ---- packed FP32 pairs (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two IEEE operations; a scalar
+// operand is broadcast by the hardware when both halves of a pair are the same register) -----------------
+#ifndef FB_EMU
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) {
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f2_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+    f2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+    f2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+    f2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+#else // SIMT-emulator build (tools/simt): two plain floats
+struct f2_t { float lo, hi; };
+inline f2_t f2_pack(float lo, float hi) { return f2_t{lo, hi}; }
+inline void f2_unpack(f2_t v, float &lo, float &hi) { lo = v.lo; hi = v.hi; }
+inline f2_t f2_fma(f2_t a, f2_t b, f2_t c) { return f2_t{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+inline f2_t f2_mul(f2_t a, f2_t b) { return f2_t{a.lo * b.lo, a.hi * b.hi}; }
+inline f2_t f2_add(f2_t a, f2_t b) { return f2_t{a.lo + b.lo, a.hi + b.hi}; }
+#endif
+__device__ __forceinline__ f2_t f2_both(float x) { return f2_pack(x, x); }
+
 // per-ray constants of the box / slab tests
 struct RayBox {
     float ix, iy, iz;    // 1/d, |d| clamped away from zero
     float ox, oy, oz;    // o/d
+    f2_t xod, yod, zod;  // (o.x, d.x) (o.y, d.y) (o.z, d.z): the two dot products of the slab test run as pairs
 };
 __device__ __forceinline__ RayBox make_raybox(const Ray &r) {
     auto inv = [](float d) {
@@ -142,38 +180,45 @@ __device__ __forceinline__ RayBox make_raybox(const Ray &r) {
     rb.ox = r.ox * rb.ix;
     rb.oy = r.oy * rb.iy;
     rb.oz = r.oz * rb.iz;
+    rb.xod = f2_pack(r.ox, r.dx);
+    rb.yod = f2_pack(r.oy, r.dy);
+    rb.zod = f2_pack(r.oz, r.dz);
     return rb;
 }
 
-// child = (a: lo.xyz | ref) (b: hi.xyz | slab_min) (c: slab_dir.xyz | slab_max)
-// AABB slab test on [0, tmax] intersected with the fitted-slab interval.  Boxes
-// and slab extents are padded at build time; the final comparison carries one
-// more relative guard band.
-#ifndef FB_TEST_ORDER
-#define FB_TEST_ORDER 0 // 0: box and slab together; 1: slab first, early out; 2: box first, early out
-#endif
+// A child record is three float4, laid out so that every pair the test works on is an aligned register pair:
+//   a = (lo.x, hi.x, lo.y, hi.y)   b = (lo.z, hi.z, slab_min, slab_max)   c = (slab_dir.xyz | ref)
+// ref >= 0: internal node index, ref < 0: triangle ~ref (leaf order).
+__device__ __forceinline__ int rec_ref(const float4 &c) { return __float_as_int(c.w); }
+
+// AABB slab test on [0, tmax] intersected with the fitted-slab interval smin <= n.(o + t d) <= smax.  Boxes
+// and slab extents are padded at build time; the final comparison carries one more relative guard band.
+// 16 of the FMA-pipe operations run as 8 packed instructions (the kernels around this are issue-bound).
 __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const float4 &a, const float4 &b,
                                           const float4 &c, float tmax) {
-    // fitted slab: smin <= n.(o + t d) <= smax
-    const float no = fmaf(c.x, r.ox, fmaf(c.y, r.oy, c.z * r.oz));
-    const float nd = fmaf(c.x, r.dx, fmaf(c.y, r.dy, c.z * r.dz));
+    (void)r;
+    // (n.o, n.d) as a pair: c.z * (oz, dz), then + c.y * (oy, dy), then + c.x * (ox, dx)
+    f2_t nod = f2_mul(f2_both(c.z), rb.zod);
+    nod = f2_fma(f2_both(c.y), rb.yod, nod);
+    nod = f2_fma(f2_both(c.x), rb.xod, nod);
+    float no, nd;
+    f2_unpack(nod, no, nd);
     float rn; // approximate reciprocal (MUFU.RCP): +-inf when the ray runs parallel to the slab
 #ifndef FB_EMU
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nd));
 #else
     rn = 1.0f / nd; // SIMT-emulator build (tools/simt); the box / slab test only has to be conservative
 #endif
-    const float s0 = (b.w - no) * rn, s1 = (c.w - no) * rn;
-    // parallel ray: (b.w-no), (c.w-no) of opposite sign -> (-inf, +inf), no clipping;
+    float s0, s1; // ((smin, smax) - no) * rn
+    f2_unpack(f2_mul(f2_add(f2_pack(b.z, b.w), f2_both(-no)), f2_both(rn)), s0, s1);
+    // parallel ray: (smin-no), (smax-no) of opposite sign -> (-inf, +inf), no clipping;
     // same sign -> both +inf or both -inf -> empty.  NaN (0*inf) is dropped by fmin/fmax.
     float tn = fmaxf(fminf(s0, s1), 0.0f);
     float tf = fminf(fmaxf(s0, s1), tmax);
-#if FB_TEST_ORDER == 1
-    if (!(tn <= tf * 1.000002f)) return false;
-#endif
-    const float x0 = fmaf(a.x, rb.ix, -rb.ox), x1 = fmaf(b.x, rb.ix, -rb.ox);
-    const float y0 = fmaf(a.y, rb.iy, -rb.oy), y1 = fmaf(b.y, rb.iy, -rb.oy);
-    const float z0 = fmaf(a.z, rb.iz, -rb.oz), z1 = fmaf(b.z, rb.iz, -rb.oz);
+    float x0, x1, y0, y1, z0, z1;
+    f2_unpack(f2_fma(f2_pack(a.x, a.y), f2_both(rb.ix), f2_both(-rb.ox)), x0, x1);
+    f2_unpack(f2_fma(f2_pack(a.z, a.w), f2_both(rb.iy), f2_both(-rb.oy)), y0, y1);
+    f2_unpack(f2_fma(f2_pack(b.x, b.y), f2_both(rb.iz), f2_both(-rb.oz)), z0, z1);
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tn));
     tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tf));
     return tn <= tf * 1.000002f;
@@ -252,7 +297,7 @@ __device__ __forceinline__ bool occluded_anyhit(const BvhView &bvh, const Ray &r
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             if (child_hit(r, rb, q[3 * c], q[3 * c + 1], q[3 * c + 2], tmax)) {
-                const int ref = __float_as_int(q[3 * c].w);
+                const int ref = rec_ref(q[3 * c + 2]);
                 if (ref < 0) {
                     const int leaf = ~ref;
                     if (leaf != target_leaf && leaf_occludes(bvh, r, tlimit, leaf, target_face)) return true;
@@ -334,7 +379,7 @@ __device__ __forceinline__ bool closest_hit(const BvhView &bvh, const Ray &r, fl
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             if (child_hit(r, rb, q[3 * c], q[3 * c + 1], q[3 * c + 2], t_best * 1.000002f)) {
-                const int ref = __float_as_int(q[3 * c].w);
+                const int ref = rec_ref(q[3 * c + 2]);
                 if (ref < 0) try_leaf(~ref);
                 else if (next < 0) next = ref;
                 else if (sp < kStackDepth) stack[sp++] = ref;

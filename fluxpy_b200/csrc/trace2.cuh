@@ -61,7 +61,7 @@ constexpr int kFifoCap = 128;  // survivors between the cull and the batches (po
 constexpr int kNodeBits = 26;  // (host check: node ids below 2^26)
 
 struct __align__(16) WarpShared {
-    float4 path[3 * kPathCap];  // records: (lo | ref) (hi | slab_min) (slab_dir | slab_max)
+    float4 path[3 * kPathCap];  // records, 3 float4 each (layout: trace.cuh child_hit)
     int2 range[kPathCap];       // leaf range of every record
     int stack[kStk][32];        // per-lane traversal stack: [level][lane]
     int cand[kCand][32];        // per-lane candidate triangles (leaf positions): [k][lane]
@@ -230,6 +230,9 @@ __device__ __forceinline__ RayBox make_raybox_fast(const Ray &r) {
     rb.ox = r.ox * rb.ix;
     rb.oy = r.oy * rb.iy;
     rb.oz = r.oz * rb.iz;
+    rb.xod = f2_pack(r.ox, r.dx);
+    rb.yod = f2_pack(r.oy, r.dy);
+    rb.zod = f2_pack(r.oz, r.dz);
     return rb;
 }
 
@@ -332,14 +335,14 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
             if (cref != -0x7fffffff) { // X is not in the list: nothing to check per record
                 for (int ks = 0; ks < nuse; ++ks, addr += 48) {
                     const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
-                    if (child_hit(ray, rb, a, b, cc, tmax_a)) push(__float_as_int(a.w));
+                    if (child_hit(ray, rb, a, b, cc, tmax_a)) push(rec_ref(cc));
                 }
             } else { // the chunk straddles several records: every lane skips the one holding its target
                 smem_addr_t raddr = (smem_addr_t)__cvta_generic_to_shared(&W->range[0]);
                 for (int ks = 0; ks < nuse; ++ks, addr += 48, raddr += 8) {
                     const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
                     const int2 rg = lds_i2(raddr);
-                    const int ref = __float_as_int(a.w);
+                    const int ref = rec_ref(cc);
                     if (tleaf >= rg.x && tleaf <= rg.y) {
                         xref = ref;
                         xbig = rg.y - rg.x + 1 > A.zone_leaves;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
                 cur = code >> 1;
                 code = A.node_up[cur];
-                if (child_hit(ray, rb, a, b, cc, tmax)) push(__float_as_int(a.w));
+                if (child_hit(ray, rb, a, b, cc, tmax)) push(rec_ref(cc));
             }
         }
         // ---- phase C: the subtrees that were actually hit, top-down, every lane on its own -------------
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 load_node<false>(bvh, node, q);
                 const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
                 const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
-                const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                const int r0 = rec_ref(q[2]), r1 = rec_ref(q[5]);
                 if (h0 && r0 < 0 && ~r0 != tleaf) push(r0);
                 if (h1 && r1 < 0 && ~r1 != tleaf) push(r1);
                 const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 load_node<false>(bvh, node, q);
                 const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
                 const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
-                const int r0 = __float_as_int(q[0].w), r1 = __float_as_int(q[3].w);
+                const int r0 = rec_ref(q[2]), r1 = rec_ref(q[5]);
                 if (h0 && r0 < 0 && ~r0 != tleaf) push(r0);
                 if (h1 && r1 < 0 && ~r1 != tleaf) push(r1);
                 const bool i0 = h0 && r0 >= 0, i1 = h1 && r1 >= 0;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                             ra[h] = __ldg(rec);
                             rb2[h] = __ldg(rec + 1);
                             rc[h] = __ldg(rec + 2);
-                            const int ref = __float_as_int(ra[h].w);
+                            const int ref = rec_ref(rc[h]);
                             rr[h] = ref < 0 ? make_int2(~ref, ~ref) : A.node_range[ref];
                         }
                     }
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                     const uint32_t m1 = __ballot_sync(0xffffffffu, 32 + lane < npath && rr[1].x <= leaf_lo && leaf_hi <= rr[1].y);
                     const int xe = m1 ? 63 - __clz(m1) : (m0 ? 31 - __clz(m0) : -1);
                     if (xe >= 0) {
-                        const int xr = __shfl_sync(0xffffffffu, __float_as_int(xe < 32 ? ra[0].w : ra[1].w), xe & 31);
+                        const int xr = __shfl_sync(0xffffffffu, __float_as_int(xe < 32 ? rc[0].w : rc[1].w), xe & 31);
                         int cur = __float_as_int(ci2.x), n2 = npath;
                         bool complete = true;
                         while (cur != xr) {
@@ -584,12 +587,13 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                         const int2 rg = rr[h];
                         bool keep = true;
                         if (A.shaft_filter && (rg.y < leaf_lo || rg.x > leaf_hi)) { // holds no target of this chunk
-                            if (a.x > h0h || b.x < h0l || a.y > h1h || b.y < h1l || a.z > h2h || b.z < h2l) keep = false;
+                            // record layout: a = (lo.x, hi.x, lo.y, hi.y), b = (lo.z, hi.z, slab_min, slab_max), cc = (dir | ref)
+                            if (a.x > h0h || a.y < h0l || a.z > h1h || a.w < h1l || b.x > h2h || b.y < h2l) keep = false;
                             const float sp = cc.x * px + cc.y * py + cc.z * pz;
                             const float lo_s = fminf(cc.x * ci0.x, cc.x * ci1.x) + fminf(cc.y * ci0.y, cc.y * ci1.y) + fminf(cc.z * ci0.z, cc.z * ci1.z);
                             const float hi_s = fmaxf(cc.x * ci0.x, cc.x * ci1.x) + fmaxf(cc.y * ci0.y, cc.y * ci1.y) + fmaxf(cc.z * ci0.z, cc.z * ci1.z);
                             const float spad = pad * (fabsf(cc.x) + fabsf(cc.y) + fabsf(cc.z));
-                            if (fminf(sp, lo_s) - spad > cc.w || fmaxf(sp, hi_s) + spad < b.w) keep = false;
+                            if (fminf(sp, lo_s) - spad > b.w || fmaxf(sp, hi_s) + spad < b.z) keep = false;
                         }
                         if (e != xdrop) {
                             keepr[h] = keep;

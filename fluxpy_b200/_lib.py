@@ -197,6 +197,7 @@ class PinnedArena:
     def __init__(self, max_free_bytes=64 << 30):
         self.free = []
         self.max_free_bytes = max_free_bytes
+        self.allocations = 0      # blocks page-locked so far (each costs ~0.4 s per GB: tests watch this)
 
     def try_take(self, nbytes):
         """A free block that fits, or None (no allocation)."""
@@ -218,6 +219,7 @@ class PinnedArena:
         p = ctypes.c_void_p()
         want = nbytes + nbytes//8 + 4096          # page-locking is slow: leave room to be reused
         check(lib().fluxb200_host_alloc(want, ctypes.byref(p)))
+        self.allocations += 1
         return _Block(p.value, want)
 
     def _give_back(self, block):

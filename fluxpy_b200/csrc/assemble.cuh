@@ -747,16 +747,18 @@ __device__ __forceinline__ double form_factor_value(double pix, double piy, doub
     const double dx = __dsub_rn(c.px, pix), dy = __dsub_rn(c.py, piy), dz = __dsub_rn(c.pz, piz);
     double a = __fma_rn(nix, dx, __fma_rn(niy, dy, __dmul_rn(niz, dz)));
     double b = -__fma_rn(c.nx, dx, __fma_rn(c.ny, dy, __dmul_rn(c.nz, dz)));
-    a = a > 0.0 ? a : 0.0;
-    b = b > 0.0 ? b : 0.0;
-    const double num = __dmul_rn(a, b); // (j == i: d == 0, so num == 0 and r2 == 0 -> 0, as row_data[i == J] = 0)
+    // max(0, a) * max(0, b) = a * b when both are positive and +0 otherwise (finite inputs): one combined
+    // test and one select of the product instead of two fp64 maxima (DSETP.MAX + FSEL + SEL + moves were 14 of
+    // the kernel's ~117 instructions per entry in the r02i capture)
+    double num = __dmul_rn(a, b); // (j == i: d == 0, so num == 0 and r2 == 0 -> 0, as row_data[i == J] = 0)
+    if (!(a > 0.0 && b > 0.0)) num = 0.0;
     const double r2 = __fma_rn(dx, dx, __fma_rn(dy, dy, __dmul_rn(dz, dz)));
     const double sden = __dmul_rn(FB_PI, __dmul_rn(r2, r2));                  // :62
     return sden == 0.0 ? 0.0 : __ddiv_rn(__dmul_rn(num, c.area), sden);     // :63-64
 }
 
 template <class T>
-__global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A) {
+__global__ void __launch_bounds__(kFillThreads, 3) emit_kernel(const FillArgs<T> A) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
     double *col_s = reinterpret_cast<double *>(stage_raw);
     auto staged = [&](int c) {
@@ -786,28 +788,85 @@ __global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A)
     const double pix = (double)Pi.x, piy = (double)Pi.y, piz = (double)Pi.z;
     const double nix = (double)Ni.x, niy = (double)Ni.y, niz = (double)Ni.z;
     constexpr int kTilesPerGroup = kFillGroup / kFillHalf, kTileWords = kFillHalf / 32;
-    for (int gh = kTilesPerGroup * g_begin; gh < kTilesPerGroup * g_end; ++gh) {
+    // The gather of a tile's columns is two dependent trips to L2 (cols[q], then P and N of that face) in front
+    // of a barrier.  float32: the NEXT tile's columns are fetched into registers (4 columns x 7 values per
+    // thread) before the current tile's entries are emitted, so those trips overlap the fp64 work instead of
+    // stalling all eight warps (long-scoreboard was the top stall, r02i / r02l captures).  float64 models keep
+    // the direct gather: 56 more registers would cost the third CTA per SM.
+    constexpr bool kPrefetch = sizeof(T) == 4;
+    constexpr int kPerThread = kFillHalf / kFillThreads;
+    Real4<T> preP[kPrefetch ? kPerThread : 1], preN[kPrefetch ? kPerThread : 1];
+    int prej[kPrefetch ? kPerThread : 1]; // ... and the face ids one tile further ahead (the first of the two trips)
+    auto fetch_ids = [&](int q0) {
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            const int q = q0 + threadIdx.x + k * kFillThreads;
+            if (q < A.n) prej[k] = A.cols[q];
+        }
+    };
+    auto fetch = [&](int q0) { // P, N of the faces whose ids are in prej
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k) {
+            const int q = q0 + threadIdx.x + k * kFillThreads;
+            if (q < A.n) {
+                preP[k] = load_real4<T>(A.faceP + prej[k]);
+                preN[k] = load_real4<T>(A.faceN + prej[k]);
+            }
+        }
+    };
+    const int gh_begin = kTilesPerGroup * g_begin, gh_end = kTilesPerGroup * g_end;
+    if (kPrefetch && gh_begin * kFillHalf < A.n) {
+        fetch_ids(gh_begin * kFillHalf);
+        fetch(gh_begin * kFillHalf);
+        fetch_ids((gh_begin + 1) * kFillHalf);
+    }
+    uint32_t word_next = 0u;
+    if (live && lane < kTileWords && gh_begin * kTileWords + lane < A.nwords) word_next = jb[gh_begin * kTileWords + lane];
+    for (int gh = gh_begin; gh < gh_end; ++gh) {
         const int q0 = gh * kFillHalf; // first column of this tile
         if (q0 >= A.n) break;          // (uniform: the last tile of the last group may be empty)
         __syncthreads(); // the previous half's columns are no longer read
-        for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
-            const int q = q0 + c;
-            if (q < A.n) {
-                const int j = A.cols[q];
-                const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
-                col_s[c] = (double)Pj.x;
-                col_s[kFillHalf + c] = (double)Pj.y;
-                col_s[2 * kFillHalf + c] = (double)Pj.z;
-                col_s[3 * kFillHalf + c] = (double)Pj.w;
-                col_s[4 * kFillHalf + c] = (double)Nj.x;
-                col_s[5 * kFillHalf + c] = (double)Nj.y;
-                col_s[6 * kFillHalf + c] = (double)Nj.z;
+        if (kPrefetch) {
+#pragma unroll
+            for (int k = 0; k < kPerThread; ++k) {
+                const int c = threadIdx.x + k * kFillThreads;
+                if (q0 + c < A.n) {
+                    col_s[c] = (double)preP[k].x;
+                    col_s[kFillHalf + c] = (double)preP[k].y;
+                    col_s[2 * kFillHalf + c] = (double)preP[k].z;
+                    col_s[3 * kFillHalf + c] = (double)preP[k].w;
+                    col_s[4 * kFillHalf + c] = (double)preN[k].x;
+                    col_s[5 * kFillHalf + c] = (double)preN[k].y;
+                    col_s[6 * kFillHalf + c] = (double)preN[k].z;
+                }
+            }
+            if (gh + 1 < gh_end && q0 + kFillHalf < A.n) {
+                fetch(q0 + kFillHalf);
+                fetch_ids(q0 + 2 * kFillHalf);
+            }
+        } else {
+            for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
+                const int q = q0 + c;
+                if (q < A.n) {
+                    const int j = A.cols[q];
+                    const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
+                    col_s[c] = (double)Pj.x;
+                    col_s[kFillHalf + c] = (double)Pj.y;
+                    col_s[2 * kFillHalf + c] = (double)Pj.z;
+                    col_s[3 * kFillHalf + c] = (double)Pj.w;
+                    col_s[4 * kFillHalf + c] = (double)Nj.x;
+                    col_s[5 * kFillHalf + c] = (double)Nj.y;
+                    col_s[6 * kFillHalf + c] = (double)Nj.z;
+                }
             }
         }
         __syncthreads();
         if (!live) continue;
-        const int wi = gh * kTileWords + lane;
-        uint32_t word = (lane < kTileWords && wi < A.nwords) ? jb[wi] : 0u;
+        uint32_t word = word_next; // (fetched one tile ahead, like the columns)
+        {
+            const int wi = (gh + 1) * kTileWords + lane;
+            word_next = (gh + 1 < gh_end && lane < kTileWords && wi < A.nwords) ? jb[wi] : 0u;
+        }
         const int c = __popc(word);
         int incl = c;
 #pragma unroll

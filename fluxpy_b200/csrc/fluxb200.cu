@@ -99,6 +99,7 @@ struct fluxb200_mesh {
     int64_t dev_capacity_hint = 0;
     int out_index_width = 0; // index width of the library-owned device CSR (0: none)
     int sub_rows_opt = 512;
+    int ramp_opt = 1; // host output: ramp of short first sub-slabs + fill(k) before trace(k+1) (0: round-2 r02i behaviour)
     // host copy-out: ship the J-order visibility words instead of the column indices and let a few
     // host threads write the indices (host_expand.cpp)
     static constexpr int kHostSlots = 8; // ring of page-locked word buffers (sub-slabs in flight on the host)
@@ -767,17 +768,25 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
     // nothing to overlap, so it uses pieces 8x larger (fewer host round trips, bounded bit buffers)
     const size_t sub_want = destination == 0 ? (size_t)M->sub_rows_opt : (size_t)M->sub_rows_opt * 8;
     const size_t sub = std::max<size_t>(1, std::min<size_t>(sub_want, std::max<size_t>(m, 1)));
-    // sub-slab boundaries: full-size pieces, then a geometrically shrinking tail so that the last
+    // sub-slab boundaries: a short first piece and a doubling ramp (the copy-out, which on a host with ~85 GB/s
+    // of memory write bandwidth is the longest of the three pipelines, starts 2 ms into the call instead of 9:
+    // profiles/r02k_timeline.md), full-size pieces, then a geometrically shrinking tail so that the last
     // fill + copy-out (which no tracing overlaps) is short
     std::vector<size_t> bounds{0};
     {
         size_t pos = 0;
         const size_t min_piece = std::min(sub, std::max<size_t>(32, sub / 4)); // never above the slot size
+        if (destination == 0 && M->ramp_opt)
+            for (size_t piece = min_piece; piece < sub && m - pos >= 4 * sub; piece *= 2) {
+                pos += piece;
+                bounds.push_back(pos);
+            }
         while (pos < m) {
             const size_t rem = m - pos;
             size_t piece = sub;
             if (destination == 0 && rem <= 2 * sub) piece = std::max(min_piece, (rem + 1) / 2);
             piece = std::min(std::min(piece, sub), rem);
+            if (rem - piece < min_piece && rem <= sub) piece = rem; // no crumb at the end (a 32-row launch costs 0.9 ms)
             pos += piece;
             bounds.push_back(pos);
         }
@@ -910,6 +919,10 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
             launches += kFillLaunches;
             FB_CUDA(cudaEventRecord(M->slot_free[b], s1)); // bits / indptr of the slot are consumed
             slot_recorded = true;
+            // Host output: trace(k+1) starts when fill(k) has finished.  Left to itself the persistent trace
+            // kernel moves in behind the fill's FIRST kernel and the emit kernel only gets its SMs back when
+            // that trace retires, so every copy-out started a whole sub-slab late (r02k timeline).
+            if (destination == 0 && M->ramp_opt) FB_CUDA(cudaStreamWaitEvent(s0, M->slot_free[b], 0));
             if (destination == 0) {
                 FB_CUDA(cudaStreamWaitEvent(s2, M->slot_free[b], 0));
                 if (tl_path) FB_CUDA(cudaEventRecord(M->tl_events[4 * k + 2], s2));
@@ -1778,6 +1791,8 @@ int fluxb200_set_option(fluxb200_mesh *M, const char *name, int64_t value) {
         } else if (s == "fill_rows") {
             FB_REQUIRE(value >= -1 && value <= 8, "fill_rows out of range");
             M->fill_rows_opt = (int)value;
+        } else if (s == "pipeline_ramp") {
+            M->ramp_opt = value ? 1 : 0;
         } else if (s == "sub_rows") {
             FB_REQUIRE(value >= 1 && value <= (1 << 20), "sub_rows out of range");
             M->sub_rows_opt = (int)value;

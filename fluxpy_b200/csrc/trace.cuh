@@ -193,32 +193,51 @@ __device__ __forceinline__ int rec_ref(const float4 &c) { return __float_as_int(
 
 // AABB slab test on [0, tmax] intersected with the fitted-slab interval smin <= n.(o + t d) <= smax.  Boxes
 // and slab extents are padded at build time; the final comparison carries one more relative guard band.
-// 16 of the FMA-pipe operations run as 8 packed instructions (the kernels around this are issue-bound).
+// kPacked: 16 of the FMA-pipe operations run as 8 packed instructions; the scalar form performs the same IEEE
+// operations in the same order, so both give the same answer bit for bit (which one is faster depends on the
+// kernel around it: profiles/r02_summary.md section 1).
+#ifndef FB_PACKED
+#define FB_PACKED 1
+#endif
+template <int kPacked = FB_PACKED>
 __device__ __forceinline__ bool child_hit(const Ray &r, const RayBox &rb, const float4 &a, const float4 &b,
                                           const float4 &c, float tmax) {
-    (void)r;
-    // (n.o, n.d) as a pair: c.z * (oz, dz), then + c.y * (oy, dy), then + c.x * (ox, dx)
-    f2_t nod = f2_mul(f2_both(c.z), rb.zod);
-    nod = f2_fma(f2_both(c.y), rb.yod, nod);
-    nod = f2_fma(f2_both(c.x), rb.xod, nod);
-    float no, nd;
-    f2_unpack(nod, no, nd);
+    float no, nd, s0, s1, x0, x1, y0, y1, z0, z1;
+    if (kPacked) {
+        // (n.o, n.d) as a pair: c.z * (oz, dz), then + c.y * (oy, dy), then + c.x * (ox, dx)
+        f2_t nod = f2_mul(f2_both(c.z), rb.zod);
+        nod = f2_fma(f2_both(c.y), rb.yod, nod);
+        nod = f2_fma(f2_both(c.x), rb.xod, nod);
+        f2_unpack(nod, no, nd);
+    } else {
+        no = fmaf(c.x, r.ox, fmaf(c.y, r.oy, c.z * r.oz));
+        nd = fmaf(c.x, r.dx, fmaf(c.y, r.dy, c.z * r.dz));
+    }
     float rn; // approximate reciprocal (MUFU.RCP): +-inf when the ray runs parallel to the slab
 #ifndef FB_EMU
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nd));
 #else
     rn = 1.0f / nd; // SIMT-emulator build (tools/simt); the box / slab test only has to be conservative
 #endif
-    float s0, s1; // ((smin, smax) - no) * rn
-    f2_unpack(f2_mul(f2_add(f2_pack(b.z, b.w), f2_both(-no)), f2_both(rn)), s0, s1);
+    if (kPacked) { // ((smin, smax) - no) * rn
+        f2_unpack(f2_mul(f2_add(f2_pack(b.z, b.w), f2_both(-no)), f2_both(rn)), s0, s1);
+    } else {
+        s0 = (b.z - no) * rn;
+        s1 = (b.w - no) * rn;
+    }
     // parallel ray: (smin-no), (smax-no) of opposite sign -> (-inf, +inf), no clipping;
     // same sign -> both +inf or both -inf -> empty.  NaN (0*inf) is dropped by fmin/fmax.
     float tn = fmaxf(fminf(s0, s1), 0.0f);
     float tf = fminf(fmaxf(s0, s1), tmax);
-    float x0, x1, y0, y1, z0, z1;
-    f2_unpack(f2_fma(f2_pack(a.x, a.y), f2_both(rb.ix), f2_both(-rb.ox)), x0, x1);
-    f2_unpack(f2_fma(f2_pack(a.z, a.w), f2_both(rb.iy), f2_both(-rb.oy)), y0, y1);
-    f2_unpack(f2_fma(f2_pack(b.x, b.y), f2_both(rb.iz), f2_both(-rb.oz)), z0, z1);
+    if (kPacked) {
+        f2_unpack(f2_fma(f2_pack(a.x, a.y), f2_both(rb.ix), f2_both(-rb.ox)), x0, x1);
+        f2_unpack(f2_fma(f2_pack(a.z, a.w), f2_both(rb.iy), f2_both(-rb.oy)), y0, y1);
+        f2_unpack(f2_fma(f2_pack(b.x, b.y), f2_both(rb.iz), f2_both(-rb.oz)), z0, z1);
+    } else {
+        x0 = fmaf(a.x, rb.ix, -rb.ox), x1 = fmaf(a.y, rb.ix, -rb.ox);
+        y0 = fmaf(a.z, rb.iy, -rb.oy), y1 = fmaf(a.w, rb.iy, -rb.oy);
+        z0 = fmaf(b.x, rb.iz, -rb.oz), z1 = fmaf(b.y, rb.iz, -rb.oz);
+    }
     tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tn));
     tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tf));
     return tn <= tf * 1.000002f;

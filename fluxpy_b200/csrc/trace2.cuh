@@ -53,6 +53,13 @@ namespace fluxb200 {
 #ifndef FB_C_FORM
 #define FB_C_FORM 0 // loop form of phase C (tuning variants)
 #endif
+#ifndef FB_T2_PACKED
+// packed FP32 pairs (FFMA2 / FMUL2 / FADD2) in the box + slab test: bit 0 phases A / B, bit 1 phase C.  Same
+// results either way (trace.cuh child_hit); measured on a 4096-row slab of the 200k-face crater (r02k):
+// 0: 30.90 ms, 1: 34.88 ms, 2: 30.56 ms, 3: 33.18 ms -- the pairs pay in the two-child test of phase C, whose
+// operands arrive as aligned register quads from LDG.128, and cost in phases A / B.
+#define FB_T2_PACKED 2
+#endif
 constexpr int kPathCap = FB_KPATH; // records of the per-unit list (source path + shared target side)
 constexpr int kStk = FB_KSTK;      // traversal stack entries per lane (shared memory)
 constexpr int kCand = FB_KCAND;    // candidate triangles per lane (shared memory)
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
             if (cref != -0x7fffffff) { // X is not in the list: nothing to check per record
                 for (int ks = 0; ks < nuse; ++ks, addr += 48) {
                     const float4 a = lds_f4(addr), b = lds_f4(addr + 16), cc = lds_f4(addr + 32);
-                    if (child_hit(ray, rb, a, b, cc, tmax_a)) push(rec_ref(cc));
+                    if (child_hit<FB_T2_PACKED & 1>(ray, rb, a, b, cc, tmax_a)) push(rec_ref(cc));
                 }
             } else { // the chunk straddles several records: every lane skips the one holding its target
                 smem_addr_t raddr = (smem_addr_t)__cvta_generic_to_shared(&W->range[0]);
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                     if (tleaf >= rg.x && tleaf <= rg.y) {
                         xref = ref;
                         xbig = rg.y - rg.x + 1 > A.zone_leaves;
-                    } else if (child_hit(ray, rb, a, b, cc, tmax_a))
+                    } else if (child_hit<FB_T2_PACKED & 1>(ray, rb, a, b, cc, tmax_a))
                         push(ref);
                 }
             }
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
                 const float4 a = __ldg(rec), b = __ldg(rec + 1), cc = __ldg(rec + 2);
                 cur = code >> 1;
                 code = A.node_up[cur];
-                if (child_hit(ray, rb, a, b, cc, tmax)) push(rec_ref(cc));
+                if (child_hit<FB_T2_PACKED & 1>(ray, rb, a, b, cc, tmax)) push(rec_ref(cc));
             }
         }
         // ---- phase C: the subtrees that were actually hit, top-down, every lane on its own -------------
@@ -389,8 +396,8 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
             while (walking) {
                 float4 q[6];
                 load_node<false>(bvh, node, q);
-                const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
-                const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
+                const bool h0 = child_hit<(FB_T2_PACKED >> 1) & 1>(ray, rb, q[0], q[1], q[2], tmax);
+                const bool h1 = child_hit<(FB_T2_PACKED >> 1) & 1>(ray, rb, q[3], q[4], q[5], tmax);
                 const int r0 = rec_ref(q[2]), r1 = rec_ref(q[5]);
                 if (h0 && r0 < 0 && ~r0 != tleaf) push(r0);
                 if (h1 && r1 < 0 && ~r1 != tleaf) push(r1);
@@ -409,8 +416,8 @@ __global__ void __launch_bounds__(kTraceThreads, FB_TRACE_MIN_BLOCKS) trace2_ker
             while (true) {
                 float4 q[6];
                 load_node<false>(bvh, node, q);
-                const bool h0 = child_hit(ray, rb, q[0], q[1], q[2], tmax);
-                const bool h1 = child_hit(ray, rb, q[3], q[4], q[5], tmax);
+                const bool h0 = child_hit<(FB_T2_PACKED >> 1) & 1>(ray, rb, q[0], q[1], q[2], tmax);
+                const bool h1 = child_hit<(FB_T2_PACKED >> 1) & 1>(ray, rb, q[3], q[4], q[5], tmax);
                 const int r0 = rec_ref(q[2]), r1 = rec_ref(q[5]);
                 if (h0 && r0 < 0 && ~r0 != tleaf) push(r0);
                 if (h1 && r1 < 0 && ~r1 != tleaf) push(r1);

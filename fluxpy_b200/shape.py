@@ -332,13 +332,22 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         # entry counts (crater floor against rim), and a short buffer costs a re-trace AND a new page-locked block
         # -- 1.9 s inside a timed loop on 2 GPUs, 3.2 s on 8 with every rank locking at once (r02g, r02h)
         cap = int(min(m*n, max(1024, ratio*1.5*m*n + 4096)))
+        cap_min = int(min(cap, max(1024, ratio*1.15*m*n + 4096)))   # what a recycled block must at least hold
         while True:
             idt = index_dtype or (np.int32 if max(cap, n, m + 1) < 2**31 else np.int64)
             isz = np.dtype(idt).itemsize
-            off_idx = -(-(cap*esz)//256)*256
-            off_ptr = off_idx + -(-(cap*isz)//256)*256
+            layout = lambda c: (-(-(c*esz)//256)*256, -(-(c*esz)//256)*256 + -(-(c*isz)//256)*256)
+            off_idx, off_ptr = layout(cap)
             need = off_ptr + (m + 1)*isz
             block = _lib.arena.try_take(need)
+            if block is None and cap_min < cap:
+                # a recycled block that is a little short of the wanted headroom beats locking a new one (2 s for
+                # 5 GB): the estimate grows whenever a denser slab of this shape turns up, the block need not
+                block = _lib.arena.try_take(layout(cap_min)[1] + (m + 1)*isz)
+                if block is not None:
+                    cap = int(min(cap, (block.nbytes - (m + 1)*isz - 512)//(esz + isz)))
+                    off_idx, off_ptr = layout(cap)
+                    need = off_ptr + (m + 1)*isz
             pageable = None
             if block is None and need > self.pageable_above_bytes and (m, n) not in ratios:
                 # A large result of a call shape seen for the first time, and no recycled page-locked block
@@ -367,7 +376,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                 if block is not None:
                     _lib.arena.discard(block)
                 type(self).overflow_retries += 1
-                cap = int(min(m*n, st.nnz + st.nnz//4))      # (room for the next, denser slab of this shape)
+                cap = cap_min = int(min(m*n, st.nnz + st.nnz//4))      # (room for the next, denser slab of this shape)
                 if index_dtype is not None and np.dtype(index_dtype).itemsize == 4 and cap >= 2**31:
                     raise RuntimeError('int32 indices cannot hold this matrix')
                 continue

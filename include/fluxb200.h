@@ -246,7 +246,11 @@ int fluxb200_mesh_stream(fluxb200_mesh *mesh, void **stream);
  * the gathers are reused by later calls with the same J while P, N, A and the tree are unchanged -- the 16 / 64
  * root-block calls of CompressedFormFactorMatrix share 4 / 8 column parts),
  * "trace_variant" (2: second-generation trace kernel, csrc/trace2.cuh, the default;
- * 1: the first-generation kernel with per-lane stacks -- identical results, kept as the A/B reference). */
+ * 1: the first-generation kernel with per-lane stacks -- identical results, kept as the A/B reference),
+ * "pipeline_ramp" (host output of fluxb200_ff_assemble; 1, the default: short first sub-slabs that double up to
+ * "sub_rows", and the fill of a sub-slab completes before the next one is traced, so that the copy-out -- the
+ * longest of the three overlapped stages -- starts ~2 ms into the call; 0: equal sub-slabs, fill and next trace
+ * left to the hardware scheduler). */
 int fluxb200_set_option(fluxb200_mesh *mesh, const char *name, int64_t value);
 /* Counters of the last assembly's trace launches: out[0] rays traced (= stats.pairs_tested), and with
  * "horizon_skip" on: out[1] 32-ray batches, out[2] batches walked without the records of the source

@@ -370,8 +370,9 @@ def test_streaming_and_two_phase_paths_agree(mods):
     m, n, counts, st = sm._ff_count(I, J, 1e-5)
     ip, ix, dv, _ = sm._ff_fill_host(m, int(st.nnz), np.int32)
     ref = scipy.sparse.csr_matrix((dv, ix, ip), shape=(m, n))
-    for sub in (7, 64, 512, 4096):
+    for sub in (7, 64, 100, 512, 4096):
         sm.set_option('sub_rows', sub)
+        sm.set_option('pipeline_ramp', 0 if sub == 64 else 1)   # (short first sub-slabs, fill before the next trace)
         sm._fill_ratio = 0.05                  # force the overflow + retry path
         sm.__dict__.pop('_fill_ratio_by_shape', None)
         r0 = type(sm).overflow_retries
@@ -387,6 +388,14 @@ def test_streaming_and_two_phase_paths_agree(mods):
         sm.pageable_above_bytes = type(sm).pageable_above_bytes
         m2, n2, ip2, ix2, dv2, c2, st2 = sm._ff_assemble_host(I, J, 1e-5, want_row_counts=True)
         assert np.array_equal(c2, counts) and st2.nnz == st.nnz and st2.pairs_tested == st.pairs_tested
+        # a denser slab of the same shape raises the estimate by up to 1.3x: the recycled page-locked block is
+        # used with less headroom instead of locking a new one (2 s for the 5 GB of a 4096-row slab at 200k faces)
+        del m2, n2, ip2, ix2, dv2, c2
+        sm._fill_ratio_by_shape[(m, n)] *= 1.25
+        a0 = _lib.arena.allocations
+        _, _, ip2, ix2, dv2, _, _ = sm._ff_assemble_host(I, J, 1e-5)
+        assert _lib.arena.allocations == a0 and np.array_equal(ix2, ix) and np.array_equal(dv2, dv)
+        del ip2, ix2, dv2
         # copy-out: column indices expanded on the host from the visibility words (default) ==
         # indices copied from the device, int32 and int64
         for expand in (0, 1):

@@ -306,8 +306,11 @@ def sweep_arm(ctx, grid, dtype, rows_want, steps=3, warmup=2):
     ctx['barrier']()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    wall = []
     for s in range(warmup, warmup + steps):
+        t = time.perf_counter()
         step(s, True)
+        wall.append(round(1e3*(time.perf_counter() - t), 2))
     e1.record(stream)
     ctx['barrier']()
     ms = ctx['allmax'](e0.elapsed_time(e1))
@@ -320,7 +323,7 @@ def sweep_arm(ctx, grid, dtype, rows_want, steps=3, warmup=2):
     return {'faces': int(nf), 'grid': grid, 'dtype': 'f64' if dtype == np.float64 else 'f32', 'rows_per_step_per_gpu': rows,
             'steps': steps, 'pairs_per_s': tested/(ms/1e3), 'pairs_all_per_s': pairs/(ms/1e3), 'ms_per_step': ms/steps,
             'trace_ms_per_launch': 1e3*trace_s, 'fill_ms_per_step': acc['fill_ms']/steps,
-            'prepare_ms_per_step': acc['prepare_ms']/steps, 'roofline_frac': fl/trace_s/1e12/peak,
+            'prepare_ms_per_step': acc['prepare_ms']/steps, 'step_ms_wall_rank0': wall, 'roofline_frac': fl/trace_s/1e12/peak,
             'roofline_peak_tflops': peak}
 
 

@@ -732,6 +732,9 @@ template <class T> struct FillArgs {
 // busy and the kernel at 20 % of the HBM write bandwidth) -- the gather through `cols` and the L2 reads
 // are shared by the 8 rows; then every warp emits its row's entries of the half, two entries per lane
 // and iteration (independent fp64 chains).
+#ifndef FB_EMIT_PER_LANE
+#define FB_EMIT_PER_LANE 2
+#endif
 constexpr int kFillGroup = 1024;
 constexpr int kFillHalf = 1024; // columns staged at a time (= one group; 512 halved the lanes of the bit expansion)
 // staged columns, structure of arrays: px[512] py[512] pz[512] area[512] nx[512] ny[512] nz[512] (doubles).
@@ -758,7 +761,7 @@ __device__ __forceinline__ double form_factor_value(double pix, double piy, doub
 }
 
 template <class T>
-__global__ void __launch_bounds__(kFillThreads, 3) emit_kernel(const FillArgs<T> A) {
+__global__ void __launch_bounds__(kFillThreads) emit_kernel(const FillArgs<T> A) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
     double *col_s = reinterpret_cast<double *>(stage_raw);
     auto staged = [&](int c) {
@@ -788,85 +791,32 @@ __global__ void __launch_bounds__(kFillThreads, 3) emit_kernel(const FillArgs<T>
     const double pix = (double)Pi.x, piy = (double)Pi.y, piz = (double)Pi.z;
     const double nix = (double)Ni.x, niy = (double)Ni.y, niz = (double)Ni.z;
     constexpr int kTilesPerGroup = kFillGroup / kFillHalf, kTileWords = kFillHalf / 32;
-    // The gather of a tile's columns is two dependent trips to L2 (cols[q], then P and N of that face) in front
-    // of a barrier.  float32: the NEXT tile's columns are fetched into registers (4 columns x 7 values per
-    // thread) before the current tile's entries are emitted, so those trips overlap the fp64 work instead of
-    // stalling all eight warps (long-scoreboard was the top stall, r02i / r02l captures).  float64 models keep
-    // the direct gather: 56 more registers would cost the third CTA per SM.
-    constexpr bool kPrefetch = sizeof(T) == 4;
-    constexpr int kPerThread = kFillHalf / kFillThreads;
-    Real4<T> preP[kPrefetch ? kPerThread : 1], preN[kPrefetch ? kPerThread : 1];
-    int prej[kPrefetch ? kPerThread : 1]; // ... and the face ids one tile further ahead (the first of the two trips)
-    auto fetch_ids = [&](int q0) {
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            const int q = q0 + threadIdx.x + k * kFillThreads;
-            if (q < A.n) prej[k] = A.cols[q];
-        }
-    };
-    auto fetch = [&](int q0) { // P, N of the faces whose ids are in prej
-#pragma unroll
-        for (int k = 0; k < kPerThread; ++k) {
-            const int q = q0 + threadIdx.x + k * kFillThreads;
-            if (q < A.n) {
-                preP[k] = load_real4<T>(A.faceP + prej[k]);
-                preN[k] = load_real4<T>(A.faceN + prej[k]);
-            }
-        }
-    };
+    // (Fetching the next tile's columns into registers ahead of the emission was measured, r02m: long-scoreboard
+    // stalls 2.6 -> 1.0 warps per issue, short-scoreboard 1.9 -> 2.9, 2.30 ms against 2.26 -- the kernel waits on
+    // its fp64 chains and shared-memory reads, not on the gather.  Not kept.)
     const int gh_begin = kTilesPerGroup * g_begin, gh_end = kTilesPerGroup * g_end;
-    if (kPrefetch && gh_begin * kFillHalf < A.n) {
-        fetch_ids(gh_begin * kFillHalf);
-        fetch(gh_begin * kFillHalf);
-        fetch_ids((gh_begin + 1) * kFillHalf);
-    }
-    uint32_t word_next = 0u;
-    if (live && lane < kTileWords && gh_begin * kTileWords + lane < A.nwords) word_next = jb[gh_begin * kTileWords + lane];
     for (int gh = gh_begin; gh < gh_end; ++gh) {
         const int q0 = gh * kFillHalf; // first column of this tile
         if (q0 >= A.n) break;          // (uniform: the last tile of the last group may be empty)
         __syncthreads(); // the previous half's columns are no longer read
-        if (kPrefetch) {
-#pragma unroll
-            for (int k = 0; k < kPerThread; ++k) {
-                const int c = threadIdx.x + k * kFillThreads;
-                if (q0 + c < A.n) {
-                    col_s[c] = (double)preP[k].x;
-                    col_s[kFillHalf + c] = (double)preP[k].y;
-                    col_s[2 * kFillHalf + c] = (double)preP[k].z;
-                    col_s[3 * kFillHalf + c] = (double)preP[k].w;
-                    col_s[4 * kFillHalf + c] = (double)preN[k].x;
-                    col_s[5 * kFillHalf + c] = (double)preN[k].y;
-                    col_s[6 * kFillHalf + c] = (double)preN[k].z;
-                }
-            }
-            if (gh + 1 < gh_end && q0 + kFillHalf < A.n) {
-                fetch(q0 + kFillHalf);
-                fetch_ids(q0 + 2 * kFillHalf);
-            }
-        } else {
-            for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
-                const int q = q0 + c;
-                if (q < A.n) {
-                    const int j = A.cols[q];
-                    const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
-                    col_s[c] = (double)Pj.x;
-                    col_s[kFillHalf + c] = (double)Pj.y;
-                    col_s[2 * kFillHalf + c] = (double)Pj.z;
-                    col_s[3 * kFillHalf + c] = (double)Pj.w;
-                    col_s[4 * kFillHalf + c] = (double)Nj.x;
-                    col_s[5 * kFillHalf + c] = (double)Nj.y;
-                    col_s[6 * kFillHalf + c] = (double)Nj.z;
-                }
+        for (int c = threadIdx.x; c < kFillHalf; c += kFillThreads) {
+            const int q = q0 + c;
+            if (q < A.n) {
+                const int j = A.cols[q];
+                const Real4<T> Pj = load_real4<T>(A.faceP + j), Nj = load_real4<T>(A.faceN + j);
+                col_s[c] = (double)Pj.x;
+                col_s[kFillHalf + c] = (double)Pj.y;
+                col_s[2 * kFillHalf + c] = (double)Pj.z;
+                col_s[3 * kFillHalf + c] = (double)Pj.w;
+                col_s[4 * kFillHalf + c] = (double)Nj.x;
+                col_s[5 * kFillHalf + c] = (double)Nj.y;
+                col_s[6 * kFillHalf + c] = (double)Nj.z;
             }
         }
         __syncthreads();
         if (!live) continue;
-        uint32_t word = word_next; // (fetched one tile ahead, like the columns)
-        {
-            const int wi = (gh + 1) * kTileWords + lane;
-            word_next = (gh + 1 < gh_end && lane < kTileWords && wi < A.nwords) ? jb[wi] : 0u;
-        }
+        const int wi = gh * kTileWords + lane;
+        uint32_t word = (lane < kTileWords && wi < A.nwords) ? jb[wi] : 0u;
         const int c = __popc(word);
         int incl = c;
 #pragma unroll
@@ -882,26 +832,28 @@ __global__ void __launch_bounds__(kFillThreads, 3) emit_kernel(const FillArgs<T>
             word &= word - 1;
         }
         __syncwarp();
-        for (int e = lane; e < total; e += 64) {
-            const int e1 = e + 32;
-            const bool two = e1 < total;
-            const int c0 = (int)list_s[warp][e], c1 = two ? (int)list_s[warp][e1] : c0;
-            const double v0 = form_factor_value(pix, piy, piz, nix, niy, niz, staged(c0));
-            const double v1 = form_factor_value(pix, piy, piz, nix, niy, niz, staged(c1));
+        for (int e = lane; e < total; e += 32 * FB_EMIT_PER_LANE) {
+            // FB_EMIT_PER_LANE independent entries per lane and iteration (2; 3 and 4 measured the same 3.14 ms of
+            // fill per slab, r02o: the kernel waits on its fp64 chains and on shared-memory reads -- wait 2.8,
+            // short-scoreboard 1.9 warps per issue -- whatever the number of chains the compiler is offered)
+            int cc[FB_EMIT_PER_LANE];
+            double vv[FB_EMIT_PER_LANE];
+#pragma unroll
+            for (int u = 0; u < FB_EMIT_PER_LANE; ++u) cc[u] = (int)list_s[warp][min(e + 32 * u, total - 1)];
+#pragma unroll
+            for (int u = 0; u < FB_EMIT_PER_LANE; ++u) vv[u] = form_factor_value(pix, piy, piz, nix, niy, niz, staged(cc[u]));
             // streaming stores: the CSR is written once and must not push the mesh and BVH, which a
             // concurrently running trace kernel lives on, out of L2
             const int64_t dst = off + e;
-            __stcs(A.data + dst, (T)v0);
-            if (two) __stcs(A.data + dst + 32, (T)v1);
-            if (A.indices) {
-                if (A.index_width == 4) {
-                    __stcs(reinterpret_cast<int *>(A.indices) + dst, q0 + c0);
-                    if (two) __stcs(reinterpret_cast<int *>(A.indices) + dst + 32, q0 + c1);
-                } else {
-                    __stcs(reinterpret_cast<long long *>(A.indices) + dst, (long long)(q0 + c0));
-                    if (two) __stcs(reinterpret_cast<long long *>(A.indices) + dst + 32, (long long)(q0 + c1));
+#pragma unroll
+            for (int u = 0; u < FB_EMIT_PER_LANE; ++u)
+                if (e + 32 * u < total) {
+                    __stcs(A.data + dst + 32 * u, (T)vv[u]);
+                    if (A.indices) {
+                        if (A.index_width == 4) __stcs(reinterpret_cast<int *>(A.indices) + dst + 32 * u, q0 + cc[u]);
+                        else __stcs(reinterpret_cast<long long *>(A.indices) + dst + 32 * u, (long long)(q0 + cc[u]));
+                    }
                 }
-            }
         }
         __syncwarp();
         off += total;

@@ -1,5 +1,6 @@
 // common.cuh -- error handling, small device helpers (libfluxb200, sm_100a)
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -37,10 +38,14 @@ struct DevBuf {
     size_t cap = 0;
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
+        const size_t old = cap;
         if (p) FB_CUDA(cudaFree(p));
         p = nullptr;
         cap = 0;
+        // a buffer that grows again grows by half (up to 8 GB extra): a few per cent at a time would free and
+        // allocate gigabytes call after call
         size_t want = bytes + bytes / 8 + 256;
+        if (old) want = std::max(want, old + std::min<size_t>(old / 2, (size_t)8 << 30));
         FB_CUDA(cudaMalloc(&p, want));
         cap = want;
     }

@@ -846,9 +846,14 @@ template <class T> bool ff_assemble(fluxb200_mesh *M, const int64_t *I, size_t m
         }
     if (destination == 2) {
         if (capacity <= 0)
+            // first call: 0.70 of the dense size (+ 12.5 % in the buffer) holds every slab of the bench meshes with
+            // the 25 % headroom below, so the buffers are allocated once -- growing them in a later call is a
+            // cudaFree + cudaMalloc of gigabytes, 5-45 ms in the middle of somebody's loop (r02n); 0.62 for
+            // results above 16 GB (the resident half of a 200k-face matrix on 2 GPUs must still fit)
             capacity = M->dev_capacity_hint > 0
                            ? M->dev_capacity_hint
-                           : std::max<int64_t>(1024, (int64_t)(0.62 * (double)m * (double)n));
+                           : std::max<int64_t>(1024, (int64_t)(((double)m * (double)n * 8.0 > 16e9 ? 0.62 : 0.70) *
+                                                               (double)m * (double)n));
         capacity = std::min<int64_t>(capacity, std::max<int64_t>((int64_t)m * (int64_t)n, 1));
         M->out_data.reserve(sizeof(T) * (size_t)capacity);
         M->out_indices.reserve((size_t)index_width * (size_t)capacity);

@@ -216,6 +216,8 @@ template <> __device__ __forceinline__ Real4<double> get_real4<double>(const dou
     return Real4<double>{a.x, a.y, b.x, b.y};
 }
 
+// (Measured and dropped, r02o: the cull's column loads -- 32 KB per unit, every byte used once by this SM -- through
+// L2 only (ld.global.cg) so that L1 keeps BVH records: 28.92 / 28.88 ms against 28.92 ms per slab.)
 // make_raybox (trace.cuh) with the hardware's approximate reciprocal (1 ulp) instead of three IEEE divisions
 // (~30 instructions per batch): the box test only has to be conservative, and its final comparison carries a
 // guard band of 2e-6 relative -- twenty times the error introduced here.

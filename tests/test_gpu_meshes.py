@@ -329,6 +329,34 @@ def test_device_resident_radiosity_and_steady_state(mods, dtype):
     assert same_csr(mods['ff'].get_form_factor_matrix(sm), FFh)
 
 
+def test_device_resident_slab_to_disk_roundtrip(mods, tmp_path):
+    """Next row N4: a slab that was assembled device-resident (the 8-GPU mode) goes to disk as a
+    ``scipy.sparse.save_npz`` file + manifest and loads back as the matrix the reference stores
+    (examples/gerlache/make_true_form_factor_matrix.py:34).  One rank, gloo, so it runs in the 1-GPU tier; the
+    two-rank version is in test_gpu_multi.py."""
+    import scipy.sparse
+    import torch.distributed as dist
+    from fluxpy_b200 import sharded, io as ffio
+    V, F = mods['meshes'].gaussian_crater(24, 1, dtype=np.float32)
+    sm = mods['shape'].CudaTrimeshShapeModel(V, F, mods['meshes'].upward_normals(V, F))
+    full = mods['ff'].get_form_factor_matrix(sm)
+    mine = not dist.is_initialized()
+    if mine:
+        dist.init_process_group('gloo', init_method=f'file://{tmp_path}/rendezvous', rank=0, world_size=1)
+    try:
+        res = sharded.get_form_factor_matrix_sharded(sm, to_host=False)
+        assert res.local_csr is None and res.device_csr.nnz == full.nnz
+        prefix = str(tmp_path / 'ff')
+        ffio.save_sharded_result(prefix, res, full.shape, 1, 0)
+    finally:
+        if mine:
+            dist.destroy_process_group()
+    back = ffio.load_sharded(prefix)
+    assert same_csr(back, full) and back.dtype == full.dtype
+    assert same_csr(scipy.sparse.load_npz(ffio.slab_path(prefix, 0)), full)     # a plain save_npz file
+    assert ffio.load_manifest(prefix)['nnz'] == full.nnz
+
+
 @pytest.mark.parametrize('scale', [1.0, 25.0, 1000.0])
 def test_culling_structures_are_conservative_at_scale(mods, scale):
     """Every culling device of the trace kernel -- fitted slabs, the per-unit

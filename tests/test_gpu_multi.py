@@ -49,6 +49,16 @@ assert nit == nref and np.allclose(B, Bref, rtol=1e-13, atol=1e-10)
 T = solve.compute_steady_state_temp(resd.device_csr, E, 0.2, 0.95)
 Tref = radiosity.compute_steady_state_temp(full, E, 0.2, 0.95)
 assert np.linalg.norm(T - Tref) <= 1e-9*np.linalg.norm(Tref)
+# N4: the device-resident slabs go to disk, one save_npz file per rank + a manifest, and load back as `full`
+from fluxpy_b200 import io as ffio
+prefix = sys.argv[5]
+ffio.save_sharded_result(prefix, resd, full.shape, world, rank)
+dist.barrier()
+if rank == 0:
+    back = ffio.load_sharded(prefix)
+    back.sort_indices()
+    assert np.array_equal(back.indptr, full.indptr) and np.array_equal(back.indices, full.indices)
+    assert np.array_equal(back.data, full.data) and ffio.load_manifest(prefix)['nnz'] == full.nnz
 dist.barrier()
 dist.destroy_process_group()
 print('ok', rank)
@@ -65,7 +75,7 @@ def test_two_rank_sharded_assembly_and_solve(tmp_path):
     s.close()
     script = tmp_path / 'worker.py'
     script.write_text(_WORKER)
-    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), '2'],
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), '2', str(tmp_path / 'ff')],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for p, o in zip(procs, outs):

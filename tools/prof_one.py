@@ -17,7 +17,9 @@ for name, value in opts:
     sm.set_option(name, int(value))
 nf = sm.num_faces
 I = np.arange(rows) + nf//2
-for rep in range(2):
+import os
+for rep in range(int(os.environ.get('PROF_ONE_REPS', '2'))):
     m, ncol, _, st = sm._ff_count(I, None, 1e-5, want_row_counts=False)
     st2 = sm._ff_fill_device(4)
+    print('rep', rep, 'trace ms %.3f fill ms %.3f' % (st.ms_trace, st2.ms_fill), flush=True)
 print(st.as_dict(), st2.ms_fill, sm.trace_counters())

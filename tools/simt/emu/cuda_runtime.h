@@ -206,6 +206,7 @@ inline unsigned long max(unsigned long a, unsigned long b) { return a > b ? a : 
 
 // ---- memory ---------------------------------------------------------------------------------------
 template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcg(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
 template <class T> inline void __stcg(T *p, T v) { *p = v; }
 inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)p; }

@@ -6,6 +6,8 @@ library in-tree with nvcc for sm_100a.
 """
 import ctypes
 import os
+import sys
+import time
 import subprocess
 
 import numpy as np
@@ -218,8 +220,12 @@ class PinnedArena:
             return best
         p = ctypes.c_void_p()
         want = nbytes + nbytes//8 + 4096          # page-locking is slow: leave room to be reused
+        t0 = time.perf_counter()
         check(lib().fluxb200_host_alloc(want, ctypes.byref(p)))
         self.allocations += 1
+        if os.environ.get('FLUXB200_ARENA_LOG'):     # diagnostic: who page-locks what, and how long it takes
+            sys.stderr.write('[fluxb200 arena] locked %.3f GB in %.2f s (block %d; free blocks: %s)\n' % (
+                want/1e9, time.perf_counter() - t0, self.allocations, [round(b.nbytes/1e9, 3) for b in self.free]))
         return _Block(p.value, want)
 
     def _give_back(self, block):

@@ -10,6 +10,9 @@ here, ``CudaTrimeshShapeModel``, answers every hook from ``libfluxb200.so``
 instead of once per row.  No Embree, no CGAL, no CPU fallback.
 """
 import ctypes
+import os
+import sys
+import time
 from abc import ABC
 
 import numpy as np
@@ -333,6 +336,12 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
         # -- 1.9 s inside a timed loop on 2 GPUs, 3.2 s on 8 with every rank locking at once (r02g, r02h)
         cap = int(min(m*n, max(1024, ratio*1.5*m*n + 4096)))
         cap_min = int(min(cap, max(1024, ratio*1.15*m*n + 4096)))   # what a recycled block must at least hold
+        # ... and what a NEW page-locked block of a repeating call shape is made for: twice the densest slab seen so
+        # far.  Blocks live long and are handed round; one sized after a sparse rim slab was later too small for
+        # the crater floor and had to be replaced inside a timed step (2.8 s, 2 GPUs, r02s)
+        cap_new = int(min(m*n, max(cap, ratio*2.0*m*n + 4096))) if (m, n) in ratios else cap
+        if cap < 2**31 <= cap_new:
+            cap_new = 2**31 - 1                                     # (keep int32 indices when they fit)
         while True:
             idt = index_dtype or (np.int32 if max(cap, n, m + 1) < 2**31 else np.int64)
             isz = np.dtype(idt).itemsize
@@ -359,11 +368,20 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                 base, dest = pageable.ctypes.data, 3
                 type(self).pageable_results += 1
             else:
-                block = block or _lib.arena.take(need)
+                if block is None:
+                    cap = max(cap, cap_new)
+                    off_idx, off_ptr = layout(cap)
+                    need = off_ptr + (m + 1)*isz
+                    block = _lib.arena.take(need)
                 base, dest = block.ptr, 0
+            t_call = time.perf_counter()
             rc = L.fluxb200_ff_assemble(self._handle, _lib.ptr(I), m, _lib.ptr(J), n, float(eps), isz, dest,
                                         base + off_ptr, base + off_idx, base, cap,
                                         _lib.ptr(counts), ctypes.byref(st))
+            if os.environ.get('FLUXB200_ARENA_LOG'):
+                sys.stderr.write('[fluxb200 assemble] %dx%d ratio %.3f cap %.3f of dense (%s) -> rc %d, nnz %.3f of dense, %.1f ms\n' % (
+                    m, n, ratio, cap/max(m*n, 1), 'pageable' if pageable is not None else 'block %.3f GB' % (block.nbytes/1e9),
+                    rc, st.nnz/max(m*n, 1), 1e3*(time.perf_counter() - t_call)))
             if pageable is not None and rc != _lib.OVERFLOW:
                 _lib.check(rc)
                 nnz = int(st.nnz)
@@ -376,7 +394,7 @@ class CudaTrimeshShapeModel(TrimeshShapeModel):
                 if block is not None:
                     _lib.arena.discard(block)
                 type(self).overflow_retries += 1
-                cap = cap_min = int(min(m*n, st.nnz + st.nnz//4))      # (room for the next, denser slab of this shape)
+                cap = cap_min = cap_new = int(min(m*n, st.nnz + st.nnz//4))   # (room for the next, denser slab of this shape)
                 if index_dtype is not None and np.dtype(index_dtype).itemsize == 4 and cap >= 2**31:
                     raise RuntimeError('int32 indices cannot hold this matrix')
                 continue

@@ -51,6 +51,10 @@ def build(force=False, verbose=False):
     deps = [os.path.join(CSRC, f) for f in sources()] + \
         [os.path.join(HERE, 'emu', f) for f in os.listdir(os.path.join(HERE, 'emu'))] + \
         [os.path.join(ROOT, 'include', 'fluxb200.h'), os.path.abspath(__file__)]
+    defs = os.environ.get('FLUXB200_EMU_DEFS', '').split()   # e.g. "-DFB_KEXPAND=12 -DFB_EXPAND_LEAVES=16": tuning variants
+    stamp = os.path.join(BUILD, 'defs.txt')
+    if (open(stamp).read() if os.path.exists(stamp) else '') != ' '.join(defs):
+        force = True
     if (not force and os.path.exists(SO_PATH)
             and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(d) for d in deps)):
         return SO_PATH
@@ -70,7 +74,7 @@ def build(force=False, verbose=False):
     cxx = os.environ.get('CXX', 'g++')
     flags = ['-std=c++17', '-O2', '-g1', '-fPIC', '-pthread', '-ffp-contract=off', '-fno-fast-math', '-mfma',
              '-fno-strict-aliasing', '-Wall', '-Wno-unknown-pragmas', '-Wno-unused-variable', '-Wno-unused-function',
-             '-Wno-unused-but-set-variable', '-I', os.path.join(HERE, 'emu')]
+             '-Wno-unused-but-set-variable', '-I', os.path.join(HERE, 'emu')] + defs
     objs = []
     for src, extra in ((os.path.join(dst, 'fluxb200.cu'), ['-x', 'c++']),
                        (os.path.join(dst, 'host_expand.cpp'), []),
@@ -88,6 +92,8 @@ def build(force=False, verbose=False):
     if out.returncode:
         print(out.stdout + out.stderr)
         raise RuntimeError('linking libfluxb200_emu.so failed')
+    with open(stamp, 'w') as fh:
+        fh.write(' '.join(defs))
     return SO_PATH
 
 

@@ -142,3 +142,66 @@ def test_fuzz_kernels_against_the_oracle(emu_lib):
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'simt', 'fuzz.py'), '25', '500000'],
                          cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and 'fuzz ok' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+_SHARDED_WORKER = r'''
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+sys.path.insert(0, os.path.join(sys.argv[1], 'tools', 'simt'))
+import build_emu
+from fluxpy_b200 import _lib
+_lib.SO_PATH = build_emu.build()            # test infrastructure: the kernels' own source on the SIMT emulator
+import torch.distributed as dist
+rank, world = int(sys.argv[3]), int(sys.argv[4])
+dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{sys.argv[2]}', rank=rank, world_size=world)
+import fluxpy_b200
+from fluxpy_b200 import meshes, sharded, io as ffio
+V, F = meshes.gaussian_crater(14, 3, dtype=np.float32)
+sm = fluxpy_b200.CudaTrimeshShapeModel(V, F, meshes.upward_normals(V, F))
+nf = sm.num_faces
+full = fluxpy_b200.get_form_factor_matrix(sm)                       # the one-process answer, on every rank
+for weights in (None, np.diff(full.indptr)):                        # equal slabs / slabs balanced by row counts
+    res = sharded.get_form_factor_matrix_sharded(sm, weights=weights)
+    assert np.array_equal(res.global_indptr, full.indptr.astype(np.int64))
+    mine = full[res.row_start:res.row_stop]
+    assert np.array_equal(res.local_csr.indptr, mine.indptr) and np.array_equal(res.local_csr.indices, mine.indices)
+    assert np.array_equal(res.local_csr.data, mine.data) and res.nnz_offset == full.indptr[res.row_start]
+# an index subset in caller order, sharded
+I = np.random.default_rng(5).permutation(nf)[:nf//2]
+resI = sharded.get_form_factor_matrix_sharded(sm, I)
+sub = full[I][resI.row_start:resI.row_stop]
+sub.sort_indices()
+assert np.array_equal(resI.local_csr.data, sub.data) and np.array_equal(resI.local_csr.indices, sub.indices)
+# device-resident slabs -> one file per rank + manifest -> the reference's matrix
+resd = sharded.get_form_factor_matrix_sharded(sm, to_host=False)
+prefix = sys.argv[5]
+ffio.save_sharded_result(prefix, resd, full.shape, world, rank)
+dist.barrier()
+if rank == 0:
+    back = ffio.load_sharded(prefix)
+    back.sort_indices()
+    assert np.array_equal(back.indptr, full.indptr) and np.array_equal(back.indices, full.indices)
+    assert np.array_equal(back.data, full.data)
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_row_sharded_assembly_on_two_ranks(emu_lib, tmp_path):
+    """SURVEY section 8e on the CPU tier: two gloo ranks, each with its own (emulated) device library, assemble
+    their row slabs; slabs, global indptr, index subsets and the slab files equal the one-process matrix.  The
+    NCCL version of this runs on two B200s (tests/test_gpu_multi.py), which a one-GPU test box skips."""
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / 'sharded_worker.py'
+    script.write_text(_SHARDED_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r), '2', str(tmp_path / 'ff')],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=900)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]

@@ -314,3 +314,42 @@ def test_reference_own_unit_tests_on_the_cuda_backend():
         assert text.count(f'[{mode}] is_occluded adjudication') == 2
     assert text.count('backend != exact convex answer on 0 faces') == 4
     assert text.count('pattern identical: True') == 4
+
+
+def test_bench_host_logic(tmp_path, monkeypatch):
+    """bench.py's bookkeeping: the slab sequence covers the mesh for every rank count, the flop model is SURVEY
+    section 8d's, and `roofline.traffic` is only reported for a capture of exactly the sources that are built."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    nf, rows = 199712, 4096
+    nslabs = nf//rows
+    for world in (1, 2, 4, 8):
+        seen = set()
+        for step in range(nslabs):
+            for rank in range(world):
+                r = bench.slab_rows(step, rank, world, rows, nf)
+                assert len(r) == rows and r[0] % rows == 0 and r[-1] < nf
+                seen.add(int(r[0])//rows)
+        assert seen == set(range(nslabs))                 # stride 7 is coprime to the slab count: all slabs sampled
+        assert len({int(bench.slab_rows(0, rank, world, rows, nf)[0]) for rank in range(world)}) == world
+    # 22 flop per candidate pair + (50 ceil(log2 Nf) + 50) per traced ray + 6 per stored entry
+    assert bench.alg_flops(10, 3, 2, 199712) == 22*10 + 3*(50*18 + 50) + 6*2
+    assert bench.alg_flops(1, 1, 0, 1 << 10) == 22 + 50*10 + 50
+    # the committed capture counts only if it belongs to the sources in the tree (sources edited since: no figure) ...
+    sha = bench.source_sha16()
+    t = bench.measured_traffic()
+    if t is not None:
+        if t.get('source_sha16') == sha:
+            assert t['dram_bytes_per_launch'] > 0
+        else:
+            assert t['dram_bytes_per_launch'] is None and 'no traffic figure' in t['note']
+    # ... and a capture of other sources is refused
+    fake = tmp_path / 'profiles'
+    fake.mkdir()
+    (fake / 'r99_trace_kernel_traffic.json').write_text(json.dumps({'source_sha16': 'f'*16, 'dram_bytes_per_launch': 1}))
+    monkeypatch.setattr(bench, 'ROOT', str(tmp_path))
+    monkeypatch.setattr(bench, 'source_sha16', lambda: sha)
+    t2 = bench.measured_traffic()
+    assert t2['dram_bytes_per_launch'] is None and 'no traffic figure' in t2['note']

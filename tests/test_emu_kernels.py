@@ -77,6 +77,18 @@ def test_gpu_parity_subset_on_the_emulator_first_generation_kernel(emu_lib):
     assert out.returncode == 0 and ' passed' in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
 
+def test_host_pipeline_on_the_emulator(emu_lib):
+    """The host side of fluxb200_ff_assemble on the emulated library: sub-slab pipeline with and without the ramp,
+    overflow retry, ordinary-memory output, recycled page-locked blocks, host / device index expansion, the
+    handle's cache of prepared column sets, device-resident slab -> disk."""
+    env = dict(os.environ, FLUXB200_TEST_EMU='1')
+    out = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_parity.py', 'tests/test_gpu_meshes.py', '-m', 'gpu',
+                          '-q', '-x', '-k', 'test_streaming_and_two_phase_paths_agree or '
+                          'test_block_assembly_reuses_prepared_column_sets or test_device_resident_slab_to_disk_roundtrip',
+                          '-p', 'no:cacheprovider'], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0 and '3 passed' in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
 HORIZON_SCRIPT = r'''
 import sys, json, numpy as np
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + '/tools/simt')
